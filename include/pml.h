@@ -1,0 +1,138 @@
+/* pml.h -- C ABI of libpml.so, the B200 (sm_100a) photometric-loss library.
+ *
+ * Drop-in boundary for the hot path of MariBax/self-supervised-depth-estimation
+ * (all file:line citations are into that repository):
+ *
+ *   Trainer.generate_images_pred      trainer.py:465-515  (trainer_fusion.py:421-472,
+ *                                     trainer_fusion_v3.py:447-482, trainer_gru.py:864-908)
+ *   Trainer.compute_reprojection_loss trainer.py:517-529
+ *   Trainer.compute_losses            trainer.py:531-622  (trainer_fusion.py:488-579,
+ *                                     trainer_fusion_v3.py:498-590, trainer_gru.py:926-1023)
+ *   layers.disp_to_depth :16-25, BackprojectDepth :139-168, Project3D :171-193,
+ *   get_smooth_loss :202-215, SSIM :218-248, transformation_from_parameters :28-103
+ *
+ * The reference has no FFI / plugin layer (it is pure Python calling ATen); the entry points
+ * below are what a ctypes binding for that path binds (INTEGRATION.md shows the stub).  Rules:
+ *   - every pointer is a DEVICE pointer to contiguous fp32 (uint8 for argmin) unless noted;
+ *   - the caller (PyTorch's caching allocator) owns every buffer including the workspace: the
+ *     library never allocates, never synchronises, keeps no global mutable state, and only
+ *     enqueues work on the given stream (CUDA-graph capturable, re-entrant);
+ *   - every function returns PML_OK or a negative pml_status; nothing throws or aborts;
+ *   - there is no CPU fallback.
+ */
+#ifndef PML_H_
+#define PML_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PML_ABI_VERSION 1
+#define PML_MAX_SOURCES 4 /* source frames per target, e.g. (-1, 1, "s") = 3 */
+#define PML_MAX_PASSES 8  /* scales handled by one call */
+
+typedef struct CUstream_st* pml_stream_t; /* == cudaStream_t */
+
+typedef enum pml_status {
+    PML_OK = 0,
+    PML_ERR_INVALID = -1,     /* bad size / null pointer / misaligned pointer */
+    PML_ERR_UNSUPPORTED = -2, /* S > PML_MAX_SOURCES, non power-of-two scale ratio, ... */
+    PML_ERR_WORKSPACE = -3,   /* workspace too small (see pml_workspace_bytes) */
+    PML_ERR_CUDA = -4         /* a CUDA runtime call failed (launch error) */
+} pml_status;
+
+/* flags, mirroring the loss-affecting options (options.py:184-198) */
+#define PML_FLAG_NO_SSIM 1u      /* --no_ssim             trainer.py:523 */
+#define PML_FLAG_NO_AUTOMASK 2u  /* --disable_automasking trainer.py:556 */
+#define PML_FLAG_AVG_REPROJ 4u   /* --avg_reprojection    trainer.py:565,585 */
+
+/* One scale ("pass") of the loss: trainer.py:469 / :538 loop body. */
+typedef struct pml_pass {
+    int32_t hd, wd;            /* resolution of disp and smooth_color; H/hd == W/wd == 2^k (or 1) */
+    float smooth_weight;       /* disparity_smoothness / 2^scale (trainer.py:616) */
+    int32_t reserved;
+    const float* disp;         /* [B,1,hd,wd]  outputs[("disp", s)] */
+    const float* smooth_color; /* [B,3,hd,wd]  inputs[("color", 0, s)] (trainer.py:547) */
+    const float* noise;        /* [B,n_id,H,W] tie-break randn (trainer.py:594) or NULL => Philox(seed) */
+    uint8_t* argmin;           /* [B,H,W] out: index returned by torch.min (trainer.py:604); nullable */
+    float* depth;              /* [B,1,H,W] out: outputs[("depth",0,s)] (trainer.py:480); nullable */
+    float* warped;             /* [S,B,3,H,W] out: outputs[("color",f,s)] (trainer.py:508); nullable */
+    float* grad_disp;          /* [B,1,hd,wd] out: d loss_s / d disp_s WITHOUT the per-image mean term
+                                  of the smoothness normalisation (that constant is grad_disp_const);
+                                  forward_backward only */
+} pml_pass;
+
+/* A group of passes that share images, intrinsics and poses (all scales when
+ * v1_multiscale is off; one scale per group when it is on). */
+typedef struct pml_problem {
+    int32_t B, H, W; /* resolution of target / sources (source_scale, trainer.py:471-476) */
+    int32_t S;       /* number of source frames (reference hard-codes [-1, 1], trainer.py:482) */
+    int32_t n_pass;
+    uint32_t flags;
+    float min_depth, max_depth; /* disp_to_depth, layers.py:16-25 */
+    float eps;                  /* Project3D eps, layers.py:174 */
+    int32_t reserved;
+    uint64_t seed;                          /* Philox seed used when pass.noise == NULL */
+    const float* target;                    /* [B,3,H,W] inputs[("color",0,source_scale)] */
+    const float* sources[PML_MAX_SOURCES];  /* [B,3,H,W] inputs[("color",f,source_scale)] */
+    const float* K;                         /* [B,4,4] */
+    const float* inv_K;                     /* [B,4,4] */
+    const float* T[PML_MAX_SOURCES];        /* [B,4,4] cam_T_cam / stereo_T per source */
+    pml_pass pass[PML_MAX_PASSES];
+    float* losses;          /* [n_pass,4] out: loss_s, photometric mean, smoothness term, 0 */
+    float* grad_T;          /* [n_pass,S,B,4,4] out: d loss_s / d T_f          (forward_backward) */
+    float* grad_disp_const; /* [n_pass,B] out: per-image constant to add to grad_disp
+                               (gradient through disp.mean(), trainer.py:612)  (forward_backward) */
+} pml_problem;
+
+int pml_abi_version(void);
+const char* pml_strerror(int status);
+
+/* Bytes of device workspace the two calls below need for this problem (16-byte aligned). */
+size_t pml_workspace_bytes(const pml_problem* p);
+
+/* generate_images_pred + compute_losses, forward only: losses, argmin, optional depth/warped. */
+int pml_loss_forward(const pml_problem* p, void* workspace, size_t workspace_bytes, pml_stream_t stream);
+
+/* Same pass, additionally producing the gradients of every loss_s with respect to disp_s and
+ * T_f in the same sweep (the adjoint is evaluated while the tiles are on chip; autograd later
+ * only scales them by the incoming gradient, pml_scale_grads). */
+int pml_loss_forward_backward(const pml_problem* p, void* workspace, size_t workspace_bytes, pml_stream_t stream);
+
+/* Backward of the autograd node: grad_disp_s <- up[s] * (grad_disp_s + const[s,b]) in place and
+ * grad_T_out[f,b] = sum_s up[s] * grad_T[s,f,b].  `upstream` is a device array [n_pass]. */
+int pml_scale_grads(int32_t n_pass, int32_t B, int32_t S, const int32_t* hd, const int32_t* wd,
+                    float* const* grad_disp, const float* grad_disp_const, const float* grad_T,
+                    const float* upstream, float* grad_T_out, pml_stream_t stream);
+
+/* ---- layer-level drop-ins (layers.py signatures), each one kernel forward + one backward ---- */
+/* disp_to_depth, layers.py:16-25 */
+int pml_disp_to_depth_fwd(const float* disp, float* scaled, float* depth, int64_t n, float min_depth, float max_depth, pml_stream_t);
+int pml_disp_to_depth_bwd(const float* disp, const float* g_scaled, const float* g_depth, float* g_disp, int64_t n, float min_depth, float max_depth, pml_stream_t);
+/* BackprojectDepth.forward, layers.py:163-168: depth [B,1,H,W], inv_K [B,4,4] -> cam [B,4,H*W] */
+int pml_backproject_fwd(const float* depth, const float* inv_K, float* cam, int32_t B, int32_t H, int32_t W, pml_stream_t);
+int pml_backproject_bwd(const float* g_cam, const float* inv_K, float* g_depth, int32_t B, int32_t H, int32_t W, pml_stream_t);
+/* Project3D.forward, layers.py:182-193: points [B,4,H*W], K,T [B,4,4] -> grid [B,H,W,2] */
+int pml_project_fwd(const float* points, const float* K, const float* T, float* grid, int32_t B, int32_t H, int32_t W, float eps, pml_stream_t);
+/* g_points [B,4,H*W]; g_T_partial [B,nblk,12] + pml_project_bwd reduces it into g_T [B,4,4] */
+int pml_project_bwd(const float* points, const float* K, const float* T, const float* g_grid, float* g_points, float* g_T,
+                    void* workspace, size_t workspace_bytes, int32_t B, int32_t H, int32_t W, float eps, pml_stream_t);
+size_t pml_project_bwd_workspace_bytes(int32_t B, int32_t H, int32_t W);
+/* SSIM.forward, layers.py:234-248: x,y [B,C,H,W] -> [B,C,H,W] */
+int pml_ssim_fwd(const float* x, const float* y, float* out, int32_t planes, int32_t H, int32_t W, pml_stream_t);
+int pml_ssim_bwd(const float* x, const float* y, const float* g_out, float* g_x, float* g_y, int32_t planes, int32_t H, int32_t W, pml_stream_t);
+/* get_smooth_loss, layers.py:202-215: disp [B,1,H,W], img [B,C,H,W] -> scalar (out[0]) */
+int pml_smooth_fwd(const float* disp, const float* img, float* out, void* workspace, size_t workspace_bytes, int32_t B, int32_t C, int32_t H, int32_t W, pml_stream_t);
+int pml_smooth_bwd(const float* disp, const float* img, const float* g_out, float* g_disp, float* g_img, int32_t B, int32_t C, int32_t H, int32_t W, pml_stream_t);
+size_t pml_smooth_workspace_bytes(int32_t B, int32_t H, int32_t W);
+/* transformation_from_parameters, layers.py:28-103: axisangle,translation [B,3] -> T [B,4,4] */
+int pml_pose_fwd(const float* axisangle, const float* translation, float* T, int32_t B, int32_t invert, pml_stream_t);
+int pml_pose_bwd(const float* axisangle, const float* translation, const float* g_T, float* g_axisangle, float* g_translation, int32_t B, int32_t invert, pml_stream_t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PML_H_ */

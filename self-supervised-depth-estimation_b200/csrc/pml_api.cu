@@ -1,0 +1,258 @@
+// C-ABI entry points of libpml.so (declared in include/pml.h).  Host side only validates,
+// plans the launch shape, carves the caller-provided workspace and enqueues kernels.
+#include "pml_common.cuh"
+#include "pml_photometric.cuh"
+#include "pml_smooth.cuh"
+#include "pml_layers.cuh"
+
+#include <stdlib.h>
+
+namespace {
+
+using namespace pml;
+
+constexpr int kNumSM = 148;   // B200
+
+inline size_t align16(size_t v) { return (v + 15) & ~size_t(15); }
+
+struct Plan {
+    int NT, TW, TH, n_strips, n_chunks, cta_per_pass, n_cta, part_stride;
+    int n_id;
+    int smooth_blocks[PML_MAX_PASSES], smooth_off[PML_MAX_PASSES], smooth_total;
+    size_t off_identity, off_part, off_mean, off_smooth, total;
+};
+
+int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+int validate(const pml_problem* p, bool grad) {
+    if (!p) return PML_ERR_INVALID;
+    if (p->B < 1 || p->H < 4 || p->W < 4 || p->n_pass < 1) return PML_ERR_INVALID;
+    if (p->S < 1 || p->S > PML_MAX_SOURCES || p->n_pass > PML_MAX_PASSES) return PML_ERR_UNSUPPORTED;
+    if (!p->target || !p->K || !p->inv_K || !p->losses) return PML_ERR_INVALID;
+    if (grad && (!p->grad_T || !p->grad_disp_const)) return PML_ERR_INVALID;
+    for (int f = 0; f < p->S; ++f)
+        if (!p->sources[f] || !p->T[f]) return PML_ERR_INVALID;
+    for (int i = 0; i < p->n_pass; ++i) {
+        const pml_pass& ps = p->pass[i];
+        if (!ps.disp || !ps.smooth_color || ps.hd < 2 || ps.wd < 2) return PML_ERR_INVALID;
+        if (grad && !ps.grad_disp) return PML_ERR_INVALID;
+        if (p->H % ps.hd != 0 || p->W % ps.wd != 0) return PML_ERR_UNSUPPORTED;
+        int k = p->H / ps.hd;
+        if (p->W / ps.wd != k || (k & (k - 1)) != 0 || k > 64) return PML_ERR_UNSUPPORTED;
+    }
+    return PML_OK;
+}
+
+Plan make_plan(const pml_problem* p, bool grad) {
+    Plan pl;
+    // strip width: the candidate whose strips waste the fewest columns
+    int best_nt = 64;
+    double best_cost = 1e30;
+    const int cands[3] = {64, 96, 128};
+    for (int c = 0; c < 3; ++c) {
+        int nt = cands[c], tw = nt - 4;
+        int ns = (p->W + tw - 1) / tw;
+        double cost = (double)ns * nt / p->W;
+        if (cost < best_cost - 1e-9) { best_cost = cost; best_nt = nt; }
+    }
+    pl.NT = env_int("PML_NT", best_nt);
+    if (pl.NT < 64) pl.NT = 64;
+    if (pl.NT > 128) pl.NT = 128;
+    pl.NT = (pl.NT / 32) * 32;
+    pl.TW = pl.NT - 4;
+    pl.n_strips = (p->W + pl.TW - 1) / pl.TW;
+    // strip height: the tallest chunk that still yields ~6 CTAs per SM (4 halo rows per chunk)
+    int per_chunk = p->n_pass * p->B * pl.n_strips;
+    int want = (kNumSM * 6 + per_chunk - 1) / per_chunk;
+    if (want < 1) want = 1;
+    int th = (p->H + want - 1) / want;
+    if (th < 16) th = 16;
+    th = ((th + 7) / 8) * 8;
+    th = env_int("PML_TH", th);
+    if (th > p->H) th = p->H;
+    if (th < 4) th = 4;
+    pl.TH = th;
+    pl.n_chunks = (p->H + pl.TH - 1) / pl.TH;
+    pl.cta_per_pass = p->B * pl.n_chunks * pl.n_strips;
+    pl.n_cta = pl.cta_per_pass * p->n_pass;
+    pl.part_stride = ((1 + 12 * p->S) + 3) & ~3;
+    const bool automask = !(p->flags & PML_FLAG_NO_AUTOMASK);
+    const bool avg = (p->flags & PML_FLAG_AVG_REPROJ) != 0;
+    pl.n_id = automask ? (avg ? 1 : p->S) : 0;
+    pl.smooth_total = 0;
+    for (int i = 0; i < p->n_pass; ++i) {
+        pl.smooth_blocks[i] = (p->pass[i].hd * p->pass[i].wd + 255) / 256;
+        pl.smooth_off[i] = pl.smooth_total;
+        pl.smooth_total += pl.smooth_blocks[i] * p->B;
+    }
+    size_t off = 0;
+    pl.off_identity = off; off = align16(off + (size_t)p->B * pl.n_id * p->H * p->W * sizeof(float));
+    pl.off_part = off;     off = align16(off + (size_t)pl.n_cta * pl.part_stride * sizeof(float));
+    pl.off_mean = off;     off = align16(off + (size_t)p->n_pass * p->B * sizeof(float));
+    pl.off_smooth = off;   off = align16(off + (size_t)pl.smooth_total * 3 * sizeof(float));
+    pl.total = off;
+    (void)grad;
+    return pl;
+}
+
+template <int S, bool GRAD, bool SSIM>
+int launch_photo(const PhotoParams& pp, int n_cta, int NT, int low_cells, cudaStream_t st) {
+    size_t smem = photometric_smem_bytes<S>(NT, GRAD, low_cells);
+    if (smem > 227 * 1024) return PML_ERR_UNSUPPORTED;
+    if (cudaFuncSetAttribute(photometric_kernel<S, GRAD, SSIM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem) != cudaSuccess)
+        return PML_ERR_CUDA;
+    PML_LAUNCH((photometric_kernel<S, GRAD, SSIM>), dim3(n_cta), dim3(NT), smem, st, pp);
+    return PML_OK;
+}
+
+template <bool GRAD, bool SSIM>
+int dispatch_S(int S, const PhotoParams& pp, int n_cta, int NT, int low_cells, cudaStream_t st) {
+    switch (S) {
+        case 1: return launch_photo<1, GRAD, SSIM>(pp, n_cta, NT, low_cells, st);
+        case 2: return launch_photo<2, GRAD, SSIM>(pp, n_cta, NT, low_cells, st);
+        case 3: return launch_photo<3, GRAD, SSIM>(pp, n_cta, NT, low_cells, st);
+        case 4: return launch_photo<4, GRAD, SSIM>(pp, n_cta, NT, low_cells, st);
+    }
+    return PML_ERR_UNSUPPORTED;
+}
+
+int run_loss(const pml_problem* p, void* ws, size_t ws_bytes, cudaStream_t st, bool grad) {
+    int rc = validate(p, grad);
+    if (rc != PML_OK) return rc;
+    Plan pl = make_plan(p, grad);
+    if (!ws || ws_bytes < pl.total) return PML_ERR_WORKSPACE;
+    if ((reinterpret_cast<uintptr_t>(ws) & 15) != 0) return PML_ERR_INVALID;
+    char* base = static_cast<char*>(ws);
+    float* identity = reinterpret_cast<float*>(base + pl.off_identity);
+    float* part = reinterpret_cast<float*>(base + pl.off_part);
+    float* mean = reinterpret_cast<float*>(base + pl.off_mean);
+    float* spart = reinterpret_cast<float*>(base + pl.off_smooth);
+    const bool ssim = !(p->flags & PML_FLAG_NO_SSIM);
+
+    // 1-2. smoothness term (writes grad_disp first; the photometric kernel adds onto it)
+    SmoothParams sp;
+    sp.B = p->B; sp.n_pass = p->n_pass; sp.disp_mean = mean; sp.part = spart;
+    for (int i = 0; i < p->n_pass; ++i) {
+        const pml_pass& ps = p->pass[i];
+        sp.pass[i].disp = ps.disp; sp.pass[i].color = ps.smooth_color;
+        sp.pass[i].grad_disp = grad ? ps.grad_disp : nullptr;
+        sp.pass[i].h = ps.hd; sp.pass[i].w = ps.wd;
+        sp.pass[i].blocks = pl.smooth_blocks[i]; sp.pass[i].block_off = pl.smooth_off[i];
+        sp.pass[i].weight = ps.smooth_weight;
+    }
+    PML_LAUNCH(disp_mean_kernel, dim3(p->B, p->n_pass), dim3(512), 0, st, sp);
+    if (grad) PML_LAUNCH(smooth_kernel<true>, dim3(pl.smooth_total), dim3(256), 0, st, sp);
+    else      PML_LAUNCH(smooth_kernel<false>, dim3(pl.smooth_total), dim3(256), 0, st, sp);
+
+    // 3. identity reprojection losses (automask), once for all passes
+    if (pl.n_id > 0) {
+        dim3 g((p->W + 255) / 256, p->H, p->B);
+        const int avg = (p->flags & PML_FLAG_AVG_REPROJ) ? 1 : 0;
+        if (ssim) PML_LAUNCH(identity_kernel<true>, g, dim3(256), 0, st, p->target, p->sources[0], p->sources[1],
+                             p->sources[2], p->sources[3], identity, p->B, p->H, p->W, p->S, avg);
+        else      PML_LAUNCH(identity_kernel<false>, g, dim3(256), 0, st, p->target, p->sources[0], p->sources[1],
+                             p->sources[2], p->sources[3], identity, p->B, p->H, p->W, p->S, avg);
+    }
+
+    // 4. fused warp + loss (+ adjoint)
+    PhotoParams pp;
+    pp.B = p->B; pp.H = p->H; pp.W = p->W; pp.n_pass = p->n_pass; pp.flags = p->flags;
+    pp.min_disp = (float)(1.0 / (double)p->max_depth);                                   // layers.py:21
+    pp.disp_range = (float)(1.0 / (double)p->min_depth - 1.0 / (double)p->max_depth);     // layers.py:23
+    pp.eps = p->eps; pp.seed = p->seed;
+    pp.target = p->target; pp.K = p->K; pp.invK = p->inv_K; pp.identity = identity;
+    for (int f = 0; f < PML_MAX_SOURCES; ++f) { pp.src[f] = p->sources[f]; pp.T[f] = p->T[f]; }
+    int low_cells = 0;
+    for (int i = 0; i < p->n_pass; ++i) {
+        const pml_pass& ps = p->pass[i];
+        PassDev& d = pp.pass[i];
+        d.disp = ps.disp; d.noise = ps.noise; d.argmin = ps.argmin; d.depth = ps.depth; d.warped = ps.warped;
+        d.grad_disp = grad ? ps.grad_disp : nullptr;
+        d.hd = ps.hd; d.wd = ps.wd; d.k = p->H / ps.hd;
+        d.rscale = (float)ps.hd / (float)p->H;
+        d.low_cols = pl.TW / d.k + 3; d.low_rows = pl.TH / d.k + 3;
+        if (d.k > 1 && d.low_cols * d.low_rows > low_cells) low_cells = d.low_cols * d.low_rows;
+    }
+    pp.TW = pl.TW; pp.TH = pl.TH; pp.n_strips = pl.n_strips; pp.n_chunks = pl.n_chunks;
+    pp.cta_per_pass = pl.cta_per_pass; pp.part = part; pp.part_stride = pl.part_stride;
+    pp.inv_n = (float)(1.0 / ((double)p->B * p->H * p->W));
+    if (grad) rc = ssim ? dispatch_S<true, true>(p->S, pp, pl.n_cta, pl.NT, low_cells, st)
+                        : dispatch_S<true, false>(p->S, pp, pl.n_cta, pl.NT, low_cells, st);
+    else      rc = ssim ? dispatch_S<false, true>(p->S, pp, pl.n_cta, pl.NT, low_cells, st)
+                        : dispatch_S<false, false>(p->S, pp, pl.n_cta, pl.NT, low_cells, st);
+    if (rc != PML_OK) return rc;
+
+    // 5. fixed-order reduction of all partials
+    FinalizeParams fq;
+    fq.B = p->B; fq.S = p->S; fq.n_pass = p->n_pass; fq.cta_per_pass = pl.cta_per_pass;
+    fq.cta_per_image = pl.n_chunks * pl.n_strips; fq.part_stride = pl.part_stride; fq.with_grad = grad ? 1 : 0;
+    fq.inv_n = pp.inv_n;
+    fq.part = part; fq.K = p->K; fq.smooth_part = spart; fq.disp_mean = mean;
+    for (int i = 0; i < p->n_pass; ++i) {
+        fq.smooth_blocks[i] = pl.smooth_blocks[i]; fq.smooth_off[i] = pl.smooth_off[i];
+        fq.hd[i] = p->pass[i].hd; fq.wd[i] = p->pass[i].wd; fq.smooth_weight[i] = p->pass[i].smooth_weight;
+    }
+    fq.losses = p->losses; fq.grad_T = p->grad_T; fq.grad_disp_const = p->grad_disp_const;
+    PML_LAUNCH(finalize_kernel, dim3(1), dim3(256), 0, st, fq);
+    return cudaGetLastError() == cudaSuccess ? PML_OK : PML_ERR_CUDA;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pml_abi_version(void) { return PML_ABI_VERSION; }
+
+const char* pml_strerror(int status) {
+    switch (status) {
+        case PML_OK: return "ok";
+        case PML_ERR_INVALID: return "invalid argument (size, null or misaligned pointer)";
+        case PML_ERR_UNSUPPORTED: return "unsupported configuration";
+        case PML_ERR_WORKSPACE: return "workspace too small";
+        case PML_ERR_CUDA: return "CUDA runtime error";
+    }
+    return "unknown status";
+}
+
+size_t pml_workspace_bytes(const pml_problem* p) {
+    if (validate(p, false) != PML_OK) return 0;
+    return make_plan(p, true).total;
+}
+
+int pml_loss_forward(const pml_problem* p, void* ws, size_t ws_bytes, pml_stream_t stream) {
+    return run_loss(p, ws, ws_bytes, reinterpret_cast<cudaStream_t>(stream), false);
+}
+
+int pml_loss_forward_backward(const pml_problem* p, void* ws, size_t ws_bytes, pml_stream_t stream) {
+    return run_loss(p, ws, ws_bytes, reinterpret_cast<cudaStream_t>(stream), true);
+}
+
+int pml_scale_grads(int32_t n_pass, int32_t B, int32_t S, const int32_t* hd, const int32_t* wd,
+                    float* const* grad_disp, const float* grad_disp_const, const float* grad_T,
+                    const float* upstream, float* grad_T_out, pml_stream_t stream) {
+    if (n_pass < 1 || n_pass > PML_MAX_PASSES || B < 1 || S < 1 || S > PML_MAX_SOURCES) return PML_ERR_INVALID;
+    if (!hd || !wd || !grad_disp || !grad_disp_const || !grad_T || !upstream || !grad_T_out) return PML_ERR_INVALID;
+    pml::ScaleParams sp;
+    sp.n_pass = n_pass; sp.B = B; sp.S = S;
+    long long total = 0;
+    for (int i = 0; i < n_pass; ++i) {
+        if (!grad_disp[i]) return PML_ERR_INVALID;
+        sp.g[i] = grad_disp[i]; sp.per_image[i] = hd[i] * wd[i];
+        sp.off[i] = total;
+        total += (long long)B * hd[i] * wd[i];
+    }
+    sp.off[n_pass] = total;
+    sp.gconst = grad_disp_const; sp.gT = grad_T; sp.up = upstream; sp.gT_out = grad_T_out;
+    long long work = total + (long long)S * B * 16;
+    int blocks = (int)((work + 255) / 256);
+    PML_LAUNCH(pml::scale_grads_kernel, dim3(blocks), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), sp);
+    return cudaGetLastError() == cudaSuccess ? PML_OK : PML_ERR_CUDA;
+}
+
+}  // extern "C"
+
+#include "pml_layers_api.inc"

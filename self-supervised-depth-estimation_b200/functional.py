@@ -1,0 +1,381 @@
+"""torch.autograd.Function wrappers over the C ABI (include/pml.h).
+
+``photometric_loss`` is the fused path: one call = ``Trainer.generate_images_pred`` +
+``Trainer.compute_losses`` (trainer.py:465-622) for a group of scales that share images.  The
+CUDA sweep evaluates the loss and, when any input requires grad, its adjoint in the same pass;
+``backward`` only scales the stored gradients by the incoming ones (pml_scale_grads).
+
+PyTorch is plumbing here (device memory, current stream, autograd graph); every byte of arithmetic
+happens inside libpml.so.  Tensors must be CUDA fp32; anything else raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _cabi
+from ._cabi import (PML_FLAG_AVG_REPROJ, PML_FLAG_NO_AUTOMASK, PML_FLAG_NO_SSIM, PML_MAX_PASSES,
+                    PML_MAX_SOURCES, PmlProblem, get_library)
+
+
+def _stream_ptr(t: torch.Tensor):
+    if t.is_cuda:
+        return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+    return ctypes.c_void_p(0)
+
+
+def _check(t: torch.Tensor, name: str, lib) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a tensor" % name)
+    if t.dtype != torch.float32:
+        raise TypeError("%s must be float32 (got %s); the sm_100a kernels compute in fp32" % (name, t.dtype))
+    if not t.is_cuda and not lib.emulator:
+        raise RuntimeError("%s is on %s: libpml has no CPU path, move it to a CUDA device" % (name, t.device))
+    return t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+class _PhotometricLoss(torch.autograd.Function):
+    """inputs: cfg, then tensors laid out as
+    disps[n_pass] | Ts[S] | target | K | inv_K | sources[S] | smooth_colors[n_pass] | noise[n_pass or 0]"""
+
+    @staticmethod
+    def forward(ctx, cfg: Dict, *tensors):
+        lib = get_library()
+        n_pass, S = cfg["n_pass"], cfg["S"]
+        tensors = [_check(t, "tensor[%d]" % i, lib) for i, t in enumerate(tensors)]
+        it = iter(tensors)
+        disps = [next(it) for _ in range(n_pass)]
+        Ts = [next(it) for _ in range(S)]
+        target, K, inv_K = next(it), next(it), next(it)
+        sources = [next(it) for _ in range(S)]
+        colors = [next(it) for _ in range(n_pass)]
+        noise = [next(it) for _ in range(n_pass)] if cfg["has_noise"] else [None] * n_pass
+
+        B, C, H, W = target.shape
+        if C != 3:
+            raise ValueError("target must be [B,3,H,W]")
+        need = ctx.needs_input_grad[1:]
+        if any(need[n_pass + S:]):
+            raise NotImplementedError(
+                "gradients with respect to images / intrinsics / noise are not produced by libpml "
+                "(the reference never requests them: colour inputs carry no grad, trainer.py:233-237)")
+        want_grad = any(need[:n_pass + S])
+        dev = target.device
+        f32 = dict(device=dev, dtype=torch.float32)
+
+        prob = PmlProblem()
+        prob.B, prob.H, prob.W, prob.S, prob.n_pass = B, H, W, S, n_pass
+        prob.flags = cfg["flags"]
+        prob.min_depth, prob.max_depth, prob.eps = cfg["min_depth"], cfg["max_depth"], cfg.get("eps", 1e-7)
+        prob.seed = cfg.get("seed", 0)
+        prob.target = target.data_ptr()
+        prob.K, prob.inv_K = K.data_ptr(), inv_K.data_ptr()
+        automask = not (cfg["flags"] & PML_FLAG_NO_AUTOMASK)
+        n_id = 0 if not automask else (1 if cfg["flags"] & PML_FLAG_AVG_REPROJ else S)
+        for f in range(S):
+            if sources[f].shape != target.shape or Ts[f].shape != (B, 4, 4):
+                raise ValueError("source / pose %d has the wrong shape" % f)
+            prob.sources[f] = sources[f].data_ptr()
+            prob.T[f] = Ts[f].data_ptr()
+        if K.shape != (B, 4, 4) or inv_K.shape != (B, 4, 4):
+            raise ValueError("K / inv_K must be [B,4,4]")
+
+        emit_depth, emit_warped = cfg.get("emit_depth", ()), cfg.get("emit_warped", ())
+        argmins, depths, warpeds, gdisps = [], [], [], []
+        for i in range(n_pass):
+            d = disps[i]
+            if d.dim() != 4 or d.shape[0] != B or d.shape[1] != 1:
+                raise ValueError("disp %d must be [B,1,h,w]" % i)
+            hd, wd = d.shape[2], d.shape[3]
+            if colors[i].shape != (B, 3, hd, wd):
+                raise ValueError("smoothness colour %d must match its disparity: %s vs %s"
+                                 % (i, tuple(colors[i].shape), tuple(d.shape)))
+            ps = prob.passes[i]
+            ps.hd, ps.wd = hd, wd
+            ps.smooth_weight = cfg["smooth_weights"][i]
+            ps.disp, ps.smooth_color = d.data_ptr(), colors[i].data_ptr()
+            if noise[i] is not None:
+                if tuple(noise[i].shape) != (B, n_id, H, W):
+                    raise ValueError("noise %d must be [B,%d,H,W]" % (i, n_id))
+                ps.noise = noise[i].data_ptr()
+            am = torch.empty((B, H, W), device=dev, dtype=torch.uint8)
+            ps.argmin = am.data_ptr()
+            argmins.append(am)
+            dp = torch.empty((B, 1, H, W), **f32) if i in emit_depth else None
+            wp = torch.empty((S, B, 3, H, W), **f32) if i in emit_warped else None
+            ps.depth, ps.warped = _ptr(dp), _ptr(wp)
+            depths.append(dp)
+            warpeds.append(wp)
+            if want_grad:
+                g = torch.empty_like(d)
+                ps.grad_disp = g.data_ptr()
+                gdisps.append(g)
+        losses4 = torch.empty((n_pass, 4), **f32)
+        prob.losses = losses4.data_ptr()
+        if want_grad:
+            grad_T = torch.empty((n_pass, S, B, 4, 4), **f32)
+            grad_const = torch.empty((n_pass, B), **f32)
+            prob.grad_T, prob.grad_disp_const = grad_T.data_ptr(), grad_const.data_ptr()
+
+        ws_bytes = lib.pml_workspace_bytes(ctypes.byref(prob))
+        if ws_bytes == 0:
+            raise _cabi.PmlError("pml_workspace_bytes rejected the problem (unsupported shape: H/hd must be a "
+                                 "power of two shared by both axes, S <= %d, scales <= %d)" % (PML_MAX_SOURCES, PML_MAX_PASSES))
+        ws = torch.empty((ws_bytes + 15) // 16 * 16, device=dev, dtype=torch.uint8)
+        fn = lib.pml_loss_forward_backward if want_grad else lib.pml_loss_forward
+        lib.check(fn(ctypes.byref(prob), _ptr(ws), ws_bytes, _stream_ptr(target)),
+                  "pml_loss_forward_backward" if want_grad else "pml_loss_forward")
+
+        ctx.want_grad = want_grad
+        ctx.cfg = cfg
+        if want_grad:
+            ctx.gdisps, ctx.grad_T, ctx.grad_const = gdisps, grad_T, grad_const
+            ctx.shapes = [(d.shape[2], d.shape[3]) for d in disps]
+            ctx.B, ctx.S, ctx.consumed = B, S, False
+        loss = losses4[:, 0].clone()
+        outs = [loss, losses4] + argmins + [t for t in depths if t is not None] + [t for t in warpeds if t is not None]
+        ctx.mark_non_differentiable(*outs[1:])
+        ctx.layout = (n_pass, [t is not None for t in depths], [t is not None for t in warpeds])
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, g_loss, *unused):
+        n_pass, S = ctx.cfg["n_pass"], ctx.cfg["S"]
+        n_in = len(ctx.needs_input_grad)
+        if not ctx.want_grad:
+            return (None,) * n_in
+        if ctx.consumed:
+            raise RuntimeError("libpml photometric-loss gradients were already consumed in place by a previous "
+                               "backward(); re-run the forward pass instead of retain_graph")
+        ctx.consumed = True
+        lib = get_library()
+        up = g_loss.contiguous().to(torch.float32)
+        B = ctx.B
+        gT_out = torch.empty((S, B, 4, 4), device=up.device, dtype=torch.float32)
+        hd = (ctypes.c_int32 * n_pass)(*[s[0] for s in ctx.shapes])
+        wd = (ctypes.c_int32 * n_pass)(*[s[1] for s in ctx.shapes])
+        gptrs = (ctypes.c_void_p * n_pass)(*[g.data_ptr() for g in ctx.gdisps])
+        lib.check(lib.pml_scale_grads(n_pass, B, S, hd, wd, gptrs, _ptr(ctx.grad_const), _ptr(ctx.grad_T),
+                                      _ptr(up), _ptr(gT_out), _stream_ptr(up)), "pml_scale_grads")
+        need = ctx.needs_input_grad[1:]
+        grads: List[Optional[torch.Tensor]] = [None]
+        for i in range(n_pass):
+            grads.append(ctx.gdisps[i] if need[i] else None)
+        for f in range(S):
+            grads.append(gT_out[f] if need[n_pass + f] else None)
+        grads += [None] * (len(need) - n_pass - S)
+        return tuple(grads)
+
+
+def photometric_loss(target, sources: Sequence[torch.Tensor], K, inv_K, Ts: Sequence[torch.Tensor],
+                     disps: Sequence[torch.Tensor], smooth_colors: Sequence[torch.Tensor], *,
+                     smooth_weights: Sequence[float], min_depth=0.1, max_depth=100.0,
+                     no_ssim=False, disable_automasking=False, avg_reprojection=False,
+                     noise: Optional[Sequence[torch.Tensor]] = None, seed: int = 0,
+                     emit_depth: Sequence[int] = (), emit_warped: Sequence[int] = ()):
+    """Fused view synthesis + photometric loss for ``len(disps)`` scales sharing one image set.
+
+    Returns a dict: ``loss`` [n_pass] (differentiable w.r.t. ``disps`` and ``Ts``; element s is
+    the reference's ``losses["loss/s"]``, trainer.py:618), ``terms`` [n_pass,4] (loss, photometric
+    mean, smoothness, 0), ``argmin`` list of uint8 [B,H,W] (torch.min index, trainer.py:604),
+    ``depth`` {pass: [B,1,H,W]} and ``warped`` {pass: [S,B,3,H,W]} for the requested passes."""
+    n_pass, S = len(disps), len(sources)
+    if not (1 <= n_pass <= PML_MAX_PASSES):
+        raise ValueError("1..%d scales per call" % PML_MAX_PASSES)
+    if not (1 <= S <= PML_MAX_SOURCES):
+        raise ValueError("1..%d source frames" % PML_MAX_SOURCES)
+    if len(Ts) != S or len(smooth_colors) != n_pass or len(smooth_weights) != n_pass:
+        raise ValueError("inconsistent argument lengths")
+    flags = (PML_FLAG_NO_SSIM if no_ssim else 0) | (PML_FLAG_NO_AUTOMASK if disable_automasking else 0) | \
+            (PML_FLAG_AVG_REPROJ if avg_reprojection else 0)
+    use_noise = noise is not None and not disable_automasking
+    cfg = dict(n_pass=n_pass, S=S, flags=flags, min_depth=float(min_depth), max_depth=float(max_depth),
+               smooth_weights=[float(w) for w in smooth_weights], has_noise=use_noise, seed=int(seed) & (2 ** 64 - 1),
+               emit_depth=tuple(emit_depth), emit_warped=tuple(emit_warped))
+    tensors = list(disps) + list(Ts) + [target, K, inv_K] + list(sources) + list(smooth_colors)
+    if use_noise:
+        tensors += list(noise)
+    outs = _PhotometricLoss.apply(cfg, *tensors)
+    res = {"loss": outs[0], "terms": outs[1], "argmin": list(outs[2:2 + n_pass]), "depth": {}, "warped": {}}
+    k = 2 + n_pass
+    for i in sorted(set(emit_depth)):
+        res["depth"][i] = outs[k]
+        k += 1
+    for i in sorted(set(emit_warped)):
+        res["warped"][i] = outs[k]
+        k += 1
+    return res
+
+
+# ------------------------------------------------------------------------------------------------
+# layer-level functions (layers.py signatures)
+# ------------------------------------------------------------------------------------------------
+class _DispToDepth(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, disp, min_depth, max_depth):
+        lib = get_library()
+        disp = _check(disp, "disp", lib)
+        scaled, depth = torch.empty_like(disp), torch.empty_like(disp)
+        lib.check(lib.pml_disp_to_depth_fwd(_ptr(disp), _ptr(scaled), _ptr(depth), disp.numel(),
+                                            float(min_depth), float(max_depth), _stream_ptr(disp)), "pml_disp_to_depth_fwd")
+        ctx.save_for_backward(disp)
+        ctx.rng = (float(min_depth), float(max_depth))
+        return scaled, depth
+
+    @staticmethod
+    def backward(ctx, g_scaled, g_depth):
+        lib = get_library()
+        (disp,) = ctx.saved_tensors
+        g = torch.empty_like(disp)
+        gs = g_scaled.contiguous() if g_scaled is not None else None
+        gd = g_depth.contiguous() if g_depth is not None else None
+        lib.check(lib.pml_disp_to_depth_bwd(_ptr(disp), _ptr(gs), _ptr(gd), _ptr(g), disp.numel(),
+                                            ctx.rng[0], ctx.rng[1], _stream_ptr(disp)), "pml_disp_to_depth_bwd")
+        return g, None, None
+
+
+class _Backproject(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, depth, inv_K, H, W):
+        lib = get_library()
+        depth, inv_K = _check(depth, "depth", lib), _check(inv_K, "inv_K", lib)
+        B = inv_K.shape[0]
+        if depth.numel() != B * H * W:
+            raise ValueError("depth has %d elements, expected %d" % (depth.numel(), B * H * W))
+        cam = torch.empty((B, 4, H * W), device=depth.device, dtype=torch.float32)
+        lib.check(lib.pml_backproject_fwd(_ptr(depth), _ptr(inv_K), _ptr(cam), B, H, W, _stream_ptr(depth)),
+                  "pml_backproject_fwd")
+        ctx.save_for_backward(inv_K)
+        ctx.dims = (B, H, W, depth.shape)
+        return cam
+
+    @staticmethod
+    def backward(ctx, g_cam):
+        lib = get_library()
+        (inv_K,) = ctx.saved_tensors
+        B, H, W, shape = ctx.dims
+        g_cam = g_cam.contiguous()
+        g = torch.empty(shape, device=g_cam.device, dtype=torch.float32)
+        lib.check(lib.pml_backproject_bwd(_ptr(g_cam), _ptr(inv_K), _ptr(g), B, H, W, _stream_ptr(g_cam)),
+                  "pml_backproject_bwd")
+        return g, None, None, None
+
+
+class _Project(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, K, T, H, W, eps):
+        lib = get_library()
+        points, K, T = _check(points, "points", lib), _check(K, "K", lib), _check(T, "T", lib)
+        B = points.shape[0]
+        if points.shape != (B, 4, H * W):
+            raise ValueError("points must be [B,4,H*W]")
+        grid = torch.empty((B, H, W, 2), device=points.device, dtype=torch.float32)
+        lib.check(lib.pml_project_fwd(_ptr(points), _ptr(K), _ptr(T), _ptr(grid), B, H, W, float(eps),
+                                      _stream_ptr(points)), "pml_project_fwd")
+        ctx.save_for_backward(points, K, T)
+        ctx.dims = (B, H, W, float(eps))
+        return grid
+
+    @staticmethod
+    def backward(ctx, g_grid):
+        lib = get_library()
+        points, K, T = ctx.saved_tensors
+        B, H, W, eps = ctx.dims
+        if ctx.needs_input_grad[1]:
+            raise NotImplementedError("no gradient for the intrinsics K (never trained in the reference)")
+        g_grid = g_grid.contiguous()
+        g_pts = torch.empty_like(points)
+        g_T = torch.empty((B, 4, 4), device=points.device, dtype=torch.float32)
+        nb = lib.pml_project_bwd_workspace_bytes(B, H, W)
+        ws = torch.empty(nb, device=points.device, dtype=torch.uint8)
+        lib.check(lib.pml_project_bwd(_ptr(points), _ptr(K), _ptr(T), _ptr(g_grid), _ptr(g_pts), _ptr(g_T),
+                                      _ptr(ws), nb, B, H, W, eps, _stream_ptr(points)), "pml_project_bwd")
+        return g_pts, None, g_T, None, None, None
+
+
+class _SSIM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y):
+        lib = get_library()
+        x, y = _check(x, "x", lib), _check(y, "y", lib)
+        if x.shape != y.shape or x.dim() != 4:
+            raise ValueError("SSIM expects two [B,C,H,W] tensors of equal shape")
+        B, C, H, W = x.shape
+        out = torch.empty_like(x)
+        lib.check(lib.pml_ssim_fwd(_ptr(x), _ptr(y), _ptr(out), B * C, H, W, _stream_ptr(x)), "pml_ssim_fwd")
+        ctx.save_for_backward(x, y)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = get_library()
+        x, y = ctx.saved_tensors
+        B, C, H, W = x.shape
+        g = g.contiguous()
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gy = torch.empty_like(y) if ctx.needs_input_grad[1] else None
+        lib.check(lib.pml_ssim_bwd(_ptr(x), _ptr(y), _ptr(g), _ptr(gx), _ptr(gy), B * C, H, W, _stream_ptr(x)),
+                  "pml_ssim_bwd")
+        return gx, gy
+
+
+class _SmoothLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, disp, img):
+        lib = get_library()
+        disp, img = _check(disp, "disp", lib), _check(img, "img", lib)
+        B, C, H, W = img.shape
+        if disp.shape != (B, 1, H, W):
+            raise ValueError("disp must be [B,1,H,W] matching img")
+        out = torch.empty((), device=disp.device, dtype=torch.float32)
+        nb = lib.pml_smooth_workspace_bytes(B, H, W)
+        ws = torch.empty(nb, device=disp.device, dtype=torch.uint8)
+        lib.check(lib.pml_smooth_fwd(_ptr(disp), _ptr(img), _ptr(out), _ptr(ws), nb, B, C, H, W, _stream_ptr(disp)),
+                  "pml_smooth_fwd")
+        ctx.save_for_backward(disp, img)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = get_library()
+        disp, img = ctx.saved_tensors
+        B, C, H, W = img.shape
+        g = g.contiguous().to(torch.float32)
+        gd = torch.empty_like(disp) if ctx.needs_input_grad[0] else None
+        gi = torch.empty_like(img) if ctx.needs_input_grad[1] else None
+        lib.check(lib.pml_smooth_bwd(_ptr(disp), _ptr(img), _ptr(g), _ptr(gd), _ptr(gi), B, C, H, W, _stream_ptr(disp)),
+                  "pml_smooth_bwd")
+        return gd, gi
+
+
+class _Pose(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, axisangle, translation, invert):
+        lib = get_library()
+        aa = _check(axisangle, "axisangle", lib).reshape(-1, 3).contiguous()
+        tr = _check(translation, "translation", lib).reshape(-1, 3).contiguous()
+        B = aa.shape[0]
+        if tr.shape[0] != B:
+            raise ValueError("axisangle / translation batch mismatch")
+        T = torch.empty((B, 4, 4), device=aa.device, dtype=torch.float32)
+        lib.check(lib.pml_pose_fwd(_ptr(aa), _ptr(tr), _ptr(T), B, 1 if invert else 0, _stream_ptr(aa)), "pml_pose_fwd")
+        ctx.save_for_backward(aa, tr)
+        ctx.meta = (bool(invert), axisangle.shape, translation.shape)
+        return T
+
+    @staticmethod
+    def backward(ctx, gT):
+        lib = get_library()
+        aa, tr = ctx.saved_tensors
+        invert, sa, st = ctx.meta
+        gT = gT.contiguous()
+        ga, gt = torch.empty_like(aa), torch.empty_like(tr)
+        lib.check(lib.pml_pose_bwd(_ptr(aa), _ptr(tr), _ptr(gT), _ptr(ga), _ptr(gt), aa.shape[0], 1 if invert else 0,
+                                   _stream_ptr(aa)), "pml_pose_bwd")
+        return ga.reshape(sa), gt.reshape(st), None

@@ -1,0 +1,213 @@
+"""Drop-in replacements for the three loss methods of the reference ``Trainer`` classes.
+
+    generate_images_pred(self, inputs, outputs)      trainer.py:465-515
+    compute_reprojection_loss(self, pred, target)    trainer.py:517-529
+    compute_losses(self, inputs, outputs) -> dict    trainer.py:531-622
+
+and their copies in trainer_fusion.py:421-579, trainer_fusion_v3.py:447-590 and
+trainer_gru.py:864-1023 (4-tuple sequence keys).  ``install(trainer_module)`` monkey-patches a
+reference trainer module in place; the reference files stay untouched.
+
+Same ``self`` contract as the reference: ``self.opt.{scales,height,width,min_depth,max_depth,
+v1_multiscale,disable_automasking,avg_reprojection,predictive_mask,no_ssim,disparity_smoothness,
+pose_model_type[,len_sequence]}``, ``self.device``, ``self.num_scales``.  Same dictionary schema
+in and out: ``losses["loss/{s}"]``, ``losses["loss"]``, ``outputs["identity_selection/{s}"]``,
+``outputs[("depth", 0, s)]``; the warped images ``outputs[("color", f, s)]`` are only written when
+``self.opt.pml_emit_warped`` is set because nothing but the tensorboard image logger
+(trainer.py:679-682) reads them.
+
+Extra, optional knobs (all default to the reference's behaviour or cheaper equivalents):
+    opt.pml_sources      ordered source frames; default [-1, 1] (hard-coded at trainer.py:482,550)
+    opt.pml_variant      "trainer" | "fusion" | "fusion_v3" | "gru" (set by install())
+    opt.pml_noise        "philox": tie-break noise drawn in-kernel (default);
+                         "host": torch.randn on the CPU generator, exactly trainer.py:594-595
+    opt.pml_emit_depth   "scale0" (default; compute_depth_losses reads only that) | "all" | "none"
+    opt.pml_emit_warped  False (default) | True
+"""
+from __future__ import annotations
+
+from typing import Dict, List
+
+import torch
+import torch.nn.functional as F
+
+from . import functional as _F
+from . import layers as _L
+
+
+def _opt(opt, name, default):
+    return getattr(opt, name, default)
+
+
+def _gather(inputs, key, n_seq, cache):
+    """trainer_gru.py:890-899,943-957 concatenates per-timestep tensors on the fly; do it once."""
+    if key in cache:
+        return cache[key]
+    if n_seq and (key + (0,)) in inputs:
+        val = torch.cat([inputs[key + (i,)] for i in range(n_seq)], 0)
+    else:
+        val = inputs[key]
+    cache[key] = val
+    return val
+
+
+def _run_fused(self, inputs, outputs):
+    opt = self.opt
+    if _opt(opt, "predictive_mask", False):
+        raise NotImplementedError("predictive_mask is not on the fused path yet (SURVEY.md §8 f4)")
+    variant = _opt(opt, "pml_variant", "trainer")
+    sources = list(_opt(opt, "pml_sources", [-1, 1]))
+    n_seq = _opt(opt, "len_sequence", 0) if variant == "gru" else 0
+    H, W = opt.height, opt.width
+    scales = list(opt.scales)
+    posecnn = (variant == "trainer" and _opt(opt, "pose_model_type", "") == "posecnn")
+    per_scale_images = (opt.v1_multiscale and variant != "fusion")
+    emit_depth = _opt(opt, "pml_emit_depth", "scale0")
+    emit_warped = bool(_opt(opt, "pml_emit_warped", False))
+    noise_mode = _opt(opt, "pml_noise", "philox")
+    automask = not opt.disable_automasking
+    n_id = 0 if not automask else (1 if opt.avg_reprojection else len(sources))
+    cache: Dict = {}
+
+    # groups of scales that share images / intrinsics / poses
+    if per_scale_images or posecnn:
+        groups = [[s] for s in scales]
+    else:
+        groups = [scales]
+
+    # tie-break noise, drawn in the reference's order (one tensor per scale, trainer.py:592-595)
+    noise = {}
+    if automask and noise_mode == "host":
+        for s in scales:
+            h, w = (H // 2 ** s, W // 2 ** s) if per_scale_images else (H, W)
+            B = outputs[("disp", s)].shape[0]
+            noise[s] = torch.randn([B, n_id, h, w]).to(self.device)
+    seed = 0
+    if automask and noise_mode != "host":
+        seed = int(torch.empty((), dtype=torch.int64).random_().item())
+
+    res = {"loss": {}, "terms": {}, "argmin": {}, "n_id": n_id}
+    for group in groups:
+        src_scale = group[0] if per_scale_images else 0
+        target = _gather(inputs, ("color", 0, src_scale), n_seq, cache)
+        K = _gather(inputs, ("K", src_scale), n_seq, cache)
+        inv_K = _gather(inputs, ("inv_K", src_scale), n_seq, cache)
+        srcs = [_gather(inputs, ("color", f, src_scale), n_seq, cache) for f in sources]
+        disps, colors, weights = [], [], []
+        for s in group:
+            disps.append(outputs[("disp", s)])
+            # trainer.py:547 smooths against the colour at the disparity's own scale;
+            # trainer_fusion.py:504 against source_scale (its disparities are full-res)
+            cs = src_scale if variant == "fusion" else s
+            colors.append(_gather(inputs, ("color", 0, cs), n_seq, cache))
+            weights.append(opt.disparity_smoothness / (2 ** s))
+        Ts = []
+        for f in sources:
+            if f == "s":
+                T = inputs["stereo_T"]
+            else:
+                T = outputs[("cam_T_cam", 0, f)]
+            if posecnn and f != "s":
+                # trainer.py:490-499: translation scaled by the mean inverse depth of this scale
+                d = outputs[("disp", group[0])]
+                if not per_scale_images:
+                    d = F.interpolate(d, [H, W], mode="bilinear", align_corners=False)
+                lo, hi = 1.0 / opt.max_depth, 1.0 / opt.min_depth
+                mean_inv_depth = (lo + (hi - lo) * d).mean(3, True).mean(2, True)
+                T = _L.transformation_from_parameters(
+                    outputs[("axisangle", 0, f)][:, 0],
+                    outputs[("translation", 0, f)][:, 0] * mean_inv_depth[:, 0], f < 0)
+            Ts.append(T)
+        ed = [i for i, s in enumerate(group) if emit_depth == "all" or (emit_depth == "scale0" and s == 0)]
+        ew = list(range(len(group))) if emit_warped else []
+        out = _F.photometric_loss(
+            target, srcs, K, inv_K, Ts, disps, colors, smooth_weights=weights,
+            min_depth=opt.min_depth, max_depth=opt.max_depth, no_ssim=opt.no_ssim,
+            disable_automasking=opt.disable_automasking, avg_reprojection=opt.avg_reprojection,
+            noise=[noise[s] for s in group] if noise else None, seed=seed + 7919 * scales.index(group[0]),
+            emit_depth=ed, emit_warped=ew)
+        for i, s in enumerate(group):
+            res["loss"][s] = out["loss"][i]
+            res["terms"][s] = out["terms"][i]
+            res["argmin"][s] = out["argmin"][i]
+            if i in out["depth"]:
+                outputs[("depth", 0, s)] = out["depth"][i]
+            if i in out["warped"]:
+                for fi, f in enumerate(sources):
+                    outputs[("color", f, s)] = out["warped"][i][fi]
+                    if automask:
+                        outputs[("color_identity", f, s)] = srcs[fi]   # trainer.py:513-515
+    return res
+
+
+def generate_images_pred(self, inputs, outputs):
+    """trainer.py:465-515.  Runs the fused sweep (warp + loss + adjoint) and parks the loss terms on
+    ``self`` for :func:`compute_losses`; writes ``outputs[("depth", 0, s)]`` (and the warped images
+    when requested).  ``outputs`` only ever receives tensors, so the reference's blanket
+    ``outputs[key] = ipt.to(device)`` loop (trainer.py:369-371) keeps working."""
+    res = _run_fused(self, inputs, outputs)
+    self._pml_pending = (id(outputs), res)
+
+
+def compute_reprojection_loss(self, pred, target):
+    """trainer.py:517-529 on the layer-level kernels (used by callers outside the fused path)."""
+    l1_loss = torch.abs(target - pred).mean(1, True)
+    if self.opt.no_ssim:
+        return l1_loss
+    ssim = getattr(self, "ssim", None)
+    ssim_loss = (ssim(pred, target) if ssim is not None else _L.SSIM()(pred, target)).mean(1, True)
+    return 0.85 * ssim_loss + 0.15 * l1_loss
+
+
+def compute_losses(self, inputs, outputs):
+    """trainer.py:531-622: returns ``{"loss/{s}": ..., "loss": ...}`` and fills
+    ``outputs["identity_selection/{s}"]``."""
+    pending = getattr(self, "_pml_pending", None)
+    if pending is None or pending[0] != id(outputs):
+        res = _run_fused(self, inputs, outputs)
+    else:
+        res = pending[1]
+    self._pml_pending = None
+    losses = {}
+    total = 0
+    for s in self.opt.scales:
+        loss = res["loss"][s]
+        total = total + loss
+        losses["loss/{}".format(s)] = loss
+        if not self.opt.disable_automasking and _opt(self.opt, "pml_emit_selection", True):
+            outputs["identity_selection/{}".format(s)] = (res["argmin"][s] > res["n_id"] - 1).float()
+        outputs[("argmin", s)] = res["argmin"][s]
+    losses["loss"] = total / self.num_scales
+    return losses
+
+
+_VARIANTS = {"trainer": "trainer", "trainer_dpt": "trainer", "trainer_fusion": "fusion",
+             "trainer_fusion_v3": "fusion_v3", "trainer_gru": "gru"}
+
+
+def install(trainer_module, variant=None):
+    """Monkey-patch ``trainer_module.Trainer`` (a reference trainer module) with the fused methods
+    and its layer symbols with the libpml-backed ones.  Returns the patched class.  ``variant`` is
+    inferred from the module name (trainer / trainer_fusion / trainer_fusion_v3 / trainer_gru)."""
+    cls = getattr(trainer_module, "Trainer", trainer_module)
+    name = getattr(trainer_module, "__name__", "trainer").split(".")[-1]
+    variant = variant or _VARIANTS.get(name, "trainer")
+
+    def _gen(self, inputs, outputs):
+        if not hasattr(self.opt, "pml_variant"):
+            self.opt.pml_variant = variant
+        return generate_images_pred(self, inputs, outputs)
+
+    def _loss(self, inputs, outputs):
+        if not hasattr(self.opt, "pml_variant"):
+            self.opt.pml_variant = variant
+        return compute_losses(self, inputs, outputs)
+
+    cls.generate_images_pred = _gen
+    cls.compute_reprojection_loss = compute_reprojection_loss
+    cls.compute_losses = _loss
+    for sym in ("BackprojectDepth", "Project3D", "SSIM", "disp_to_depth", "get_smooth_loss",
+                "transformation_from_parameters"):
+        if hasattr(trainer_module, sym):
+            setattr(trainer_module, sym, getattr(_L, sym))
+    return cls
