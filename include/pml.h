@@ -86,6 +86,8 @@ typedef struct pml_problem {
     float* grad_T;          /* [n_pass,S,B,4,4] out: d loss_s / d T_f          (forward_backward) */
     float* grad_disp_const; /* [n_pass,B] out: per-image constant to add to grad_disp
                                (gradient through disp.mean(), trainer.py:612)  (forward_backward) */
+    void* prof_start;       /* optional cudaEvent_t recorded right before the fused sweep kernel */
+    void* prof_stop;        /* optional cudaEvent_t recorded right after it (bench.py roofline) */
 } pml_problem;
 
 int pml_abi_version(void);

@@ -194,10 +194,13 @@ def generate_images_pred(opt, inputs, outputs, sources=(-1, 1), variant="trainer
 
 
 def compute_losses(opt, inputs, outputs, sources=(-1, 1), variant="trainer",
-                   noise: Optional[Sequence[torch.Tensor]] = None, keep_maps=False):
+                   noise: Optional[Sequence[torch.Tensor]] = None, keep_maps=False, forced_argmin=None):
     """trainer.py:531-622 (trainer_fusion.py:488-579; trainer_fusion_v3.py:498-590;
     trainer_gru.py:926-1023).  ``noise`` = pre-drawn tie-break tensors, one per scale, in the
     order the reference draws them (trainer.py:592-595); None draws from the global generator.
+    ``forced_argmin`` ({scale: int64 [B,H,W]}) replaces the min by a gather with the given
+    selection: gradients of a candidate path are then comparable even where fp32 rounding of a
+    near-tie made the device pick the other candidate (test use only).
 
     Returns ``losses`` like the reference plus, under ``outputs``: ``identity_selection/{s}``,
     ``("argmin", s)`` (int64 [B,H,W], what the reference's ``torch.min`` returns) and, with
@@ -234,6 +237,9 @@ def compute_losses(opt, inputs, outputs, sources=(-1, 1), variant="trainer",
             idxs = torch.zeros_like(combined[:, 0], dtype=torch.int64)
         else:
             to_opt, idxs = torch.min(combined, dim=1)
+            if forced_argmin is not None:
+                idxs = forced_argmin[scale].to(torch.int64)
+                to_opt = combined.gather(1, idxs.unsqueeze(1))[:, 0]
         outputs[("argmin", scale)] = idxs
         if ident is not None:
             outputs["identity_selection/{}".format(scale)] = (idxs > ident.shape[1] - 1).to(disp.dtype)
@@ -254,7 +260,7 @@ def compute_losses(opt, inputs, outputs, sources=(-1, 1), variant="trainer",
 
 
 def run(opt, inputs, outputs, sources=(-1, 1), variant="trainer", noise=None, dtype=None,
-        want_grad=True, keep_maps=True):
+        want_grad=True, keep_maps=True, forced_argmin=None):
     """Whole path on copies of the dictionaries: fwd (+ bwd of losses["loss"]).
 
     Returns a dict: loss (float), loss/{s}, argmin/{s}, identity_selection/{s}, margin/{s},
@@ -278,7 +284,8 @@ def run(opt, inputs, outputs, sources=(-1, 1), variant="trainer", noise=None, dt
                 leaves["grad_T/{}".format(f)] = out[("cam_T_cam", 0, f)]
     nz = None if noise is None else [conv(n) for n in noise]
     generate_images_pred(opt, inp, out, sources, variant)
-    losses = compute_losses(opt, inp, out, sources, variant, nz, keep_maps=keep_maps)
+    losses = compute_losses(opt, inp, out, sources, variant, nz, keep_maps=keep_maps,
+                            forced_argmin=forced_argmin)
     res = {"loss": losses["loss"].detach()}
     for s in opt.scales:
         res["loss/{}".format(s)] = losses["loss/{}".format(s)].detach()
@@ -292,6 +299,7 @@ def run(opt, inputs, outputs, sources=(-1, 1), variant="trainer", noise=None, dt
             res["to_optimise/{}".format(s)] = out[("to_optimise", s)]
         for f in sources:
             res["color/{}/{}".format(f, s)] = out[("color", f, s)].detach()
+            res["sample/{}/{}".format(f, s)] = out[("sample", f, s)].detach()
     if want_grad:
         losses["loss"].backward()
         for name, leaf in leaves.items():

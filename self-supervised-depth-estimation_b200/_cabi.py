@@ -32,7 +32,8 @@ class PmlProblem(Structure):
                 ("target", c_void_p), ("sources", c_void_p * PML_MAX_SOURCES),
                 ("K", c_void_p), ("inv_K", c_void_p), ("T", c_void_p * PML_MAX_SOURCES),
                 ("passes", PmlPass * PML_MAX_PASSES),
-                ("losses", c_void_p), ("grad_T", c_void_p), ("grad_disp_const", c_void_p)]
+                ("losses", c_void_p), ("grad_T", c_void_p), ("grad_disp_const", c_void_p),
+                ("prof_start", c_void_p), ("prof_stop", c_void_p)]
 
 
 class PmlError(RuntimeError):

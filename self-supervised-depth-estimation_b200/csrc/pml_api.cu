@@ -6,6 +6,7 @@
 #include "pml_layers.cuh"
 
 #include <stdlib.h>
+#include <atomic>
 
 namespace {
 
@@ -21,6 +22,14 @@ struct Plan {
     int smooth_blocks[PML_MAX_PASSES], smooth_off[PML_MAX_PASSES], smooth_total;
     size_t off_identity, off_part, off_mean, off_smooth, total;
 };
+
+inline void pml_event_record(void* ev, cudaStream_t st) {
+#ifndef PML_HOST_EMU
+    cudaEventRecord(static_cast<cudaEvent_t>(ev), st);
+#else
+    (void)ev; (void)st;
+#endif
+}
 
 int env_int(const char* name, int dflt) {
     const char* s = getenv(name);
@@ -102,9 +111,16 @@ template <int S, bool GRAD, bool SSIM>
 int launch_photo(const PhotoParams& pp, int n_cta, int NT, int low_cells, cudaStream_t st) {
     size_t smem = photometric_smem_bytes<S>(NT, GRAD, low_cells);
     if (smem > 227 * 1024) return PML_ERR_UNSUPPORTED;
-    if (cudaFuncSetAttribute(photometric_kernel<S, GRAD, SSIM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)smem) != cudaSuccess)
-        return PML_ERR_CUDA;
+    // Opt in to > 48 KB dynamic shared memory.  The high-water mark is the only process-wide state
+    // of the library: monotonic, so concurrent callers can at worst repeat an idempotent call, and
+    // it keeps attribute changes out of CUDA-graph capture once the shape has been seen.
+    static std::atomic<int> configured{0};
+    if ((int)smem > configured.load(std::memory_order_relaxed)) {
+        if (cudaFuncSetAttribute(photometric_kernel<S, GRAD, SSIM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem) != cudaSuccess)
+            return PML_ERR_CUDA;
+        configured.store((int)smem, std::memory_order_relaxed);
+    }
     PML_LAUNCH((photometric_kernel<S, GRAD, SSIM>), dim3(n_cta), dim3(NT), smem, st, pp);
     return PML_OK;
 }
@@ -180,11 +196,13 @@ int run_loss(const pml_problem* p, void* ws, size_t ws_bytes, cudaStream_t st, b
     pp.TW = pl.TW; pp.TH = pl.TH; pp.n_strips = pl.n_strips; pp.n_chunks = pl.n_chunks;
     pp.cta_per_pass = pl.cta_per_pass; pp.part = part; pp.part_stride = pl.part_stride;
     pp.inv_n = (float)(1.0 / ((double)p->B * p->H * p->W));
+    if (p->prof_start) pml_event_record(p->prof_start, st);
     if (grad) rc = ssim ? dispatch_S<true, true>(p->S, pp, pl.n_cta, pl.NT, low_cells, st)
                         : dispatch_S<true, false>(p->S, pp, pl.n_cta, pl.NT, low_cells, st);
     else      rc = ssim ? dispatch_S<false, true>(p->S, pp, pl.n_cta, pl.NT, low_cells, st)
                         : dispatch_S<false, false>(p->S, pp, pl.n_cta, pl.NT, low_cells, st);
     if (rc != PML_OK) return rc;
+    if (p->prof_stop) pml_event_record(p->prof_stop, st);
 
     // 5. fixed-order reduction of all partials
     FinalizeParams fq;

@@ -123,6 +123,9 @@ class _PhotometricLoss(torch.autograd.Function):
             grad_const = torch.empty((n_pass, B), **f32)
             prob.grad_T, prob.grad_disp_const = grad_T.data_ptr(), grad_const.data_ptr()
 
+        prof = cfg.get("prof_events")
+        if prof is not None:
+            prob.prof_start, prob.prof_stop = prof[0].cuda_event, prof[1].cuda_event
         ws_bytes = lib.pml_workspace_bytes(ctypes.byref(prob))
         if ws_bytes == 0:
             raise _cabi.PmlError("pml_workspace_bytes rejected the problem (unsupported shape: H/hd must be a "
@@ -178,7 +181,7 @@ def photometric_loss(target, sources: Sequence[torch.Tensor], K, inv_K, Ts: Sequ
                      smooth_weights: Sequence[float], min_depth=0.1, max_depth=100.0,
                      no_ssim=False, disable_automasking=False, avg_reprojection=False,
                      noise: Optional[Sequence[torch.Tensor]] = None, seed: int = 0,
-                     emit_depth: Sequence[int] = (), emit_warped: Sequence[int] = ()):
+                     emit_depth: Sequence[int] = (), emit_warped: Sequence[int] = (), prof_events=None):
     """Fused view synthesis + photometric loss for ``len(disps)`` scales sharing one image set.
 
     Returns a dict: ``loss`` [n_pass] (differentiable w.r.t. ``disps`` and ``Ts``; element s is
@@ -197,7 +200,7 @@ def photometric_loss(target, sources: Sequence[torch.Tensor], K, inv_K, Ts: Sequ
     use_noise = noise is not None and not disable_automasking
     cfg = dict(n_pass=n_pass, S=S, flags=flags, min_depth=float(min_depth), max_depth=float(max_depth),
                smooth_weights=[float(w) for w in smooth_weights], has_noise=use_noise, seed=int(seed) & (2 ** 64 - 1),
-               emit_depth=tuple(emit_depth), emit_warped=tuple(emit_warped))
+               emit_depth=tuple(emit_depth), emit_warped=tuple(emit_warped), prof_events=prof_events)
     tensors = list(disps) + list(Ts) + [target, K, inv_K] + list(sources) + list(smooth_colors)
     if use_noise:
         tensors += list(noise)

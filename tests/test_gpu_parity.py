@@ -1,0 +1,148 @@
+"""Parity of the CUDA path (through the C ABI, the autograd Functions and the Trainer drop-ins)
+against the golden fixtures of the reference and the float64 CPU oracle.  Run with -m gpu."""
+import pytest
+import torch
+
+import common
+import parity
+from ssde_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", common.golden_names())
+def test_golden_fixture(cuda_lib, name):
+    variant, opt, inputs, outputs, r32, r64, seed = common.load_golden(name)
+    got = common.run_product(opt, inputs, outputs, variant, device="cuda", noise_seed=seed)
+    rep = parity.check(got, opt, variant, inputs, outputs, seed, r32, r64, degenerate=(name == "trainer_constant"))
+    print(name, {k: v for k, v in rep.items()})
+
+
+CONFIGS = {
+    # BASELINE.json configs at sizes the float64 oracle finishes in seconds
+    "c2_headline_b2": dict(B=2, H=192, W=640, sources=(-1, 1), variant="trainer", style="kitti"),
+    "c3_stereo_320x1024": dict(B=1, H=320, W=1024, sources=(-1, 1, "s"), variant="trainer", style="kitti"),
+    "c4_gru_seq5": dict(B=5, H=192, W=640, sources=(-1, 1), variant="gru", style="kitti", len_sequence=5),
+    "c5_small_96x320_s1": dict(B=3, H=96, W=320, sources=(1,), variant="trainer", style="kitti"),
+    "c5_s4": dict(B=1, H=96, W=320, sources=(-1, 1, -2, 2), variant="trainer", style="kitti"),
+    "uniform_stress": dict(B=2, H=96, W=320, sources=(-1, 1), variant="trainer", style="uniform"),
+    "out_of_frustum": dict(B=2, H=96, W=320, sources=(-1, 1), variant="trainer", style="oof"),
+    "tanh_range_disp": dict(B=2, H=64, W=160, sources=(-1, 1), variant="fusion", style="kitti", neg_disp=True),
+}
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_against_oracle(cuda_lib, name):
+    c = dict(CONFIGS[name])
+    B, H, W, sources, variant = c["B"], c["H"], c["W"], c["sources"], c["variant"]
+    opt = synthetic.make_options(H, W, batch_size=B, len_sequence=c.get("len_sequence", 1))
+    inputs, outputs = synthetic.make_batch(B, H, W, sources=sources, seed=31, style=c["style"],
+                                           full_res_disp=(variant == "fusion"))
+    if c.get("neg_disp"):
+        # Fusion's UpscalePS ends in tanh (fusion_v2.py:234-235): disparities are not confined to
+        # [0,1]; keep sigma > 0 so that depth stays finite in the oracle too
+        for s in opt.scales:
+            outputs[("disp", s)] = outputs[("disp", s)] * 1.6 - 0.0005
+    got = common.run_product(opt, inputs, outputs, variant, device="cuda", noise_seed=5, sources=sources)
+    rep = parity.check(got, opt, variant, inputs, outputs, 5, sources=sources)
+    print(name, rep)
+
+
+def _full_size(B=12, H=192, W=640, seed=0):
+    opt = synthetic.make_options(H, W, batch_size=B)
+    inputs, outputs = synthetic.make_batch(B, H, W, seed=seed)
+    return opt, inputs, outputs
+
+
+def test_full_size_determinism_and_forward_only(cuda_lib):
+    opt, inputs, outputs = _full_size()
+    a = common.run_product(opt, inputs, outputs, device="cuda", noise_seed=1)
+    b = common.run_product(opt, inputs, outputs, device="cuda", noise_seed=1)
+    c = common.run_product(opt, inputs, outputs, device="cuda", noise_seed=1, want_grad=False)
+    for s in opt.scales:
+        assert torch.equal(a["argmin/%d" % s], b["argmin/%d" % s])
+        assert torch.equal(a["argmin/%d" % s], c["argmin/%d" % s])
+        assert a["loss/%d" % s].item() == b["loss/%d" % s].item() == c["loss/%d" % s].item()
+        assert torch.equal(a["grad_disp/%d" % s], b["grad_disp/%d" % s]) or \
+            common.rel_err(a["grad_disp/%d" % s], b["grad_disp/%d" % s]) < 1e-6   # 4-way corner atomics
+    assert torch.equal(a["grad_T/1"], b["grad_T/1"])
+
+
+def test_full_size_batch_decomposition(cuda_lib):
+    """The loss is a mean over images (trainer.py:610): B=12 equals the mean of twelve B=1 runs
+    (same per-image noise), and each image's disparity gradient is 1/12 of its stand-alone one."""
+    opt, inputs, outputs = _full_size()
+    B = 12
+    seed = 3
+    full = common.run_product(opt, inputs, outputs, device="cuda", noise_seed=seed)
+    noise = synthetic.draw_noise(B, opt.height, opt.width, opt.scales, 2, seed=seed)
+    acc = {s: 0.0 for s in opt.scales}
+    from ssde_b200 import functional as Fn
+    dev = torch.device("cuda")
+    for b in (0, 5, 11):
+        sl = slice(b, b + 1)
+        disps = [outputs[("disp", s)][sl].to(dev).requires_grad_(True) for s in opt.scales]
+        out = Fn.photometric_loss(
+            inputs[("color", 0, 0)][sl].to(dev), [inputs[("color", f, 0)][sl].to(dev) for f in (-1, 1)],
+            inputs[("K", 0)][sl].to(dev), inputs[("inv_K", 0)][sl].to(dev),
+            [outputs[("cam_T_cam", 0, f)][sl].to(dev) for f in (-1, 1)], disps,
+            [inputs[("color", 0, s)][sl].to(dev) for s in opt.scales],
+            smooth_weights=[1e-3 / 2 ** s for s in opt.scales], noise=[n[sl].to(dev) for n in noise])
+        (out["loss"].sum() / len(opt.scales)).backward()
+        for i, s in enumerate(opt.scales):
+            assert torch.equal(out["argmin"][i][0].cpu(), full["argmin/%d" % s][b])
+            # photometric part scales by 1/B exactly; the smoothness normaliser B*h*(w-1) too
+            assert common.rel_err(disps[i].grad.cpu()[0] / B, full["grad_disp/%d" % s][b]) < 2e-5
+
+
+def test_full_size_gradient_linearity(cuda_lib):
+    opt, inputs, outputs = _full_size(B=4)
+    from types import SimpleNamespace
+    from ssde_b200 import trainer_hooks
+    dev = torch.device("cuda")
+    grads = []
+    for scale in (1.0, 2.5):
+        o = SimpleNamespace(**vars(opt)); o.pml_noise = "host"
+        ns = SimpleNamespace(opt=o, device=dev, num_scales=4)
+        inp = {k: v.to(dev) for k, v in inputs.items()}
+        out = {k: v.to(dev).clone() for k, v in outputs.items()}
+        out[("disp", 0)].requires_grad_(True)
+        out[("cam_T_cam", 0, 1)].requires_grad_(True)
+        torch.manual_seed(0)
+        trainer_hooks.generate_images_pred(ns, inp, out)
+        losses = trainer_hooks.compute_losses(ns, inp, out)
+        (losses["loss"] * scale).backward()
+        grads.append((out[("disp", 0)].grad.clone(), out[("cam_T_cam", 0, 1)].grad.clone()))
+    assert common.rel_err(grads[1][0].cpu(), grads[0][0].cpu() * 2.5) < 1e-6
+    assert common.rel_err(grads[1][1].cpu(), grads[0][1].cpu() * 2.5) < 1e-6
+
+
+def test_layer_dropins(cuda_lib):
+    import layer_checks
+    layer_checks.run("cuda")
+    layer_checks.run("cuda", B=3, H=40, W=300)
+
+
+def test_reference_unfused_code_path_on_dropin_layers(cuda_lib):
+    """The reference's own unfused recipe (BackprojectDepth -> Project3D -> F.grid_sample ->
+    SSIM/L1, trainer.py:501-529) written against the drop-in layers reproduces the oracle."""
+    import torch.nn.functional as F
+    from oracle import photometric_oracle as po
+    from ssde_b200 import layers as L
+    B, H, W = 2, 64, 160
+    opt = synthetic.make_options(H, W, batch_size=B)
+    inputs, outputs = synthetic.make_batch(B, H, W, seed=8)
+    dev = torch.device("cuda")
+    disp = outputs[("disp", 0)].to(dev)
+    _, depth = L.disp_to_depth(disp, opt.min_depth, opt.max_depth)
+    cam = L.BackprojectDepth(B, H, W).to(dev)(depth, inputs[("inv_K", 0)].to(dev))
+    grid = L.Project3D(B, H, W).to(dev)(cam, inputs[("K", 0)].to(dev), outputs[("cam_T_cam", 0, 1)].to(dev))
+    pred = F.grid_sample(inputs[("color", 1, 0)].to(dev), grid, padding_mode="border", align_corners=False)
+    tgt = inputs[("color", 0, 0)].to(dev)
+    rp = 0.85 * L.SSIM()(pred, tgt).mean(1, True) + 0.15 * (tgt - pred).abs().mean(1, True)
+    o = {k: v.double() for k, v in outputs.items()}
+    i = {k: v.double() for k, v in inputs.items()}
+    po.generate_images_pred(opt, i, o, sources=(1,))
+    want = po.reprojection_loss(o[("color", 1, 0)], i[("color", 0, 0)])
+    assert (rp.double().cpu() - want).abs().max().item() < 5e-4
+    assert abs(rp.mean().item() - want.mean().item()) / want.mean().item() < 1e-5
