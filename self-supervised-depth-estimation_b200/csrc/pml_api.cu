@@ -20,7 +20,8 @@ struct Plan {
     int NT, TW, TH, n_strips, n_chunks, cta_per_pass, n_cta, part_stride;
     int n_id;
     int smooth_blocks[PML_MAX_PASSES], smooth_off[PML_MAX_PASSES], smooth_total;
-    size_t off_identity, off_part, off_mean, off_smooth, total;
+    int max_chunks;
+    size_t off_identity, off_part, off_mean, off_meanpart, off_imagepart, off_smooth, total;
 };
 
 inline void pml_event_record(void* ev, cudaStream_t st) {
@@ -101,6 +102,13 @@ Plan make_plan(const pml_problem* p, bool grad) {
     pl.off_identity = off; off = align16(off + (size_t)p->B * pl.n_id * p->H * p->W * sizeof(float));
     pl.off_part = off;     off = align16(off + (size_t)pl.n_cta * pl.part_stride * sizeof(float));
     pl.off_mean = off;     off = align16(off + (size_t)p->n_pass * p->B * sizeof(float));
+    pl.max_chunks = 1;
+    for (int i = 0; i < p->n_pass; ++i) {
+        int c = (p->pass[i].hd * p->pass[i].wd + pml::kMeanChunk - 1) / pml::kMeanChunk;
+        if (c > pl.max_chunks) pl.max_chunks = c;
+    }
+    pl.off_meanpart = off; off = align16(off + (size_t)p->n_pass * p->B * pl.max_chunks * sizeof(float));
+    pl.off_imagepart = off; off = align16(off + (size_t)p->n_pass * p->B * 4 * sizeof(float));
     pl.off_smooth = off;   off = align16(off + (size_t)pl.smooth_total * 3 * sizeof(float));
     pl.total = off;
     (void)grad;
@@ -147,11 +155,14 @@ int run_loss(const pml_problem* p, void* ws, size_t ws_bytes, cudaStream_t st, b
     float* part = reinterpret_cast<float*>(base + pl.off_part);
     float* mean = reinterpret_cast<float*>(base + pl.off_mean);
     float* spart = reinterpret_cast<float*>(base + pl.off_smooth);
+    float* meanpart = reinterpret_cast<float*>(base + pl.off_meanpart);
+    float* imagepart = reinterpret_cast<float*>(base + pl.off_imagepart);
     const bool ssim = !(p->flags & PML_FLAG_NO_SSIM);
 
     // 1-2. smoothness term (writes grad_disp first; the photometric kernel adds onto it)
     SmoothParams sp;
     sp.B = p->B; sp.n_pass = p->n_pass; sp.disp_mean = mean; sp.part = spart;
+    sp.mean_part = meanpart; sp.max_chunks = pl.max_chunks;
     for (int i = 0; i < p->n_pass; ++i) {
         const pml_pass& ps = p->pass[i];
         sp.pass[i].disp = ps.disp; sp.pass[i].color = ps.smooth_color;
@@ -160,7 +171,7 @@ int run_loss(const pml_problem* p, void* ws, size_t ws_bytes, cudaStream_t st, b
         sp.pass[i].blocks = pl.smooth_blocks[i]; sp.pass[i].block_off = pl.smooth_off[i];
         sp.pass[i].weight = ps.smooth_weight;
     }
-    PML_LAUNCH(disp_mean_kernel, dim3(p->B, p->n_pass), dim3(512), 0, st, sp);
+    PML_LAUNCH(disp_sum_kernel, dim3(pl.max_chunks, p->B, p->n_pass), dim3(256), 0, st, sp);
     if (grad) PML_LAUNCH(smooth_kernel<true>, dim3(pl.smooth_total), dim3(256), 0, st, sp);
     else      PML_LAUNCH(smooth_kernel<false>, dim3(pl.smooth_total), dim3(256), 0, st, sp);
 
@@ -215,7 +226,9 @@ int run_loss(const pml_problem* p, void* ws, size_t ws_bytes, cudaStream_t st, b
         fq.hd[i] = p->pass[i].hd; fq.wd[i] = p->pass[i].wd; fq.smooth_weight[i] = p->pass[i].smooth_weight;
     }
     fq.losses = p->losses; fq.grad_T = p->grad_T; fq.grad_disp_const = p->grad_disp_const;
-    PML_LAUNCH(finalize_kernel, dim3(1), dim3(256), 0, st, fq);
+    fq.image_part = imagepart;
+    PML_LAUNCH(finalize_image_kernel, dim3(p->B, p->n_pass), dim3(128), 0, st, fq);
+    PML_LAUNCH(finalize_loss_kernel, dim3(p->n_pass), dim3(32), 0, st, fq);
     return cudaGetLastError() == cudaSuccess ? PML_OK : PML_ERR_CUDA;
 }
 

@@ -585,7 +585,8 @@ inline size_t photometric_smem_bytes(int NT, bool grad, int low_cells) {
 
 // ---------------------------------------------------------------------------------------------
 // finalize: fixed-order reduction of the per-CTA partials into losses / grad_T, plus the
-// smoothness partials (see pml_smooth.cuh).  One CTA; the work is a few thousand floats.
+// smoothness partials (see pml_smooth.cuh).  Stage 1: one CTA per (image, scale); stage 2: one warp
+// per scale combines the images.  The work is a few thousand floats.
 // ---------------------------------------------------------------------------------------------
 struct FinalizeParams {
     int B, S, n_pass, cta_per_pass, cta_per_image, part_stride, with_grad;
@@ -598,87 +599,71 @@ struct FinalizeParams {
     const float* disp_mean;    // [n_pass][B]
     int hd[PML_MAX_PASSES], wd[PML_MAX_PASSES];
     float smooth_weight[PML_MAX_PASSES];
+    float* image_part;         // [n_pass][B][4]: photometric sum, smooth x sum, smooth y sum, -
     float* losses;             // [n_pass][4]
     float* grad_T;             // [n_pass][S][B][16]
     float* grad_disp_const;    // [n_pass][B]
 };
 
-__global__ void __launch_bounds__(256)
-finalize_kernel(const FinalizeParams q) {
-    __shared__ float s_sm[2][PML_MAX_PASSES];
-    const int tid = threadIdx.x, nt = blockDim.x;
-    // photometric loss per pass: strided fixed-order sum, then a serial combine by thread 0
-    __shared__ float s_tmp[256];
-    for (int pi = 0; pi < q.n_pass; ++pi) {
+__global__ void __launch_bounds__(128)
+finalize_image_kernel(const FinalizeParams q) {
+    __shared__ float s_col[1 + 12 * PML_MAX_SOURCES];
+    __shared__ float s_w[4][3];
+    const int tid = threadIdx.x, b = blockIdx.x, pi = blockIdx.y;
+    const int ncol = q.with_grad ? 1 + 12 * q.S : 1;
+    // photometric partial columns of this image's CTAs, summed in CTA order
+    if (tid < ncol) {
+        const float* base = q.part + (size_t)(pi * q.cta_per_pass + b * q.cta_per_image) * q.part_stride + tid;
         float v = 0.f;
-        for (int i = tid; i < q.cta_per_pass; i += nt)
-            v += q.part[(size_t)(pi * q.cta_per_pass + i) * q.part_stride];
-        s_tmp[tid] = v;
-        __syncthreads();
-        for (int st = nt / 2; st > 0; st >>= 1) {
-            if (tid < st) s_tmp[tid] += s_tmp[tid + st];
-            __syncthreads();
-        }
-        if (tid == 0) s_sm[0][pi] = s_tmp[0] * q.inv_n;
-        __syncthreads();
+        for (int c = 0; c < q.cta_per_image; ++c) v += base[(size_t)c * q.part_stride];
+        s_col[tid] = v;
     }
-    // smoothness loss per pass (sum over images and blocks), and the per-image mean-path constant
-    for (int pi = 0; pi < q.n_pass; ++pi) {
-        const int nb = q.smooth_blocks[pi];
-        const float* sp = q.smooth_part + (size_t)q.smooth_off[pi] * 3;
-        float vx = 0.f, vy = 0.f;
-        for (int i = tid; i < q.B * nb; i += nt) { vx += sp[i * 3]; vy += sp[i * 3 + 1]; }
-        s_tmp[tid] = vx;
-        __syncthreads();
-        for (int st = nt / 2; st > 0; st >>= 1) { if (tid < st) s_tmp[tid] += s_tmp[tid + st]; __syncthreads(); }
-        float sx = s_tmp[0];
-        __syncthreads();
-        s_tmp[tid] = vy;
-        __syncthreads();
-        for (int st = nt / 2; st > 0; st >>= 1) { if (tid < st) s_tmp[tid] += s_tmp[tid + st]; __syncthreads(); }
-        float sy = s_tmp[0];
-        __syncthreads();
-        if (tid == 0) {
-            const float h = (float)q.hd[pi], w = (float)q.wd[pi];
-            float nx = (float)q.B * h * (w - 1.f), ny = (float)q.B * (h - 1.f) * w;
-            s_sm[1][pi] = sx / nx + sy / ny;   // layers.py:215
-        }
-        if (q.with_grad && tid < q.B) {
-            float g = 0.f;
-            for (int i = 0; i < nb; ++i) g += sp[(tid * nb + i) * 3 + 2];   // sum_xy g_n * disp
-            const float m = q.disp_mean[pi * q.B + tid] + 1e-7f;
+    // smoothness partials of this image
+    const int nb = q.smooth_blocks[pi];
+    const float* sp = q.smooth_part + ((size_t)q.smooth_off[pi] + (size_t)b * nb) * 3;
+    float vx = 0.f, vy = 0.f, vg = 0.f;
+    for (int i = tid; i < nb; i += blockDim.x) { vx += sp[i * 3]; vy += sp[i * 3 + 1]; vg += sp[i * 3 + 2]; }
+    vx = warp_sum(vx); vy = warp_sum(vy); vg = warp_sum(vg);
+    if ((tid & 31) == 0) { s_w[tid >> 5][0] = vx; s_w[tid >> 5][1] = vy; s_w[tid >> 5][2] = vg; }
+    __syncthreads();
+    if (tid == 0) {
+        float sx = 0.f, sy = 0.f, sg = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { sx += s_w[w][0]; sy += s_w[w][1]; sg += s_w[w][2]; }
+        float* ip = q.image_part + (size_t)(pi * q.B + b) * 4;
+        ip[0] = s_col[0]; ip[1] = sx; ip[2] = sy; ip[3] = 0.f;
+        if (q.with_grad) {
+            const float m = q.disp_mean[pi * q.B + b] + 1e-7f;
             // d/d mean of disp/(mean+eps): -sum(g_n*disp)/(mean+eps)^2, spread by 1/(h*w)
-            q.grad_disp_const[pi * q.B + tid] =
-                -q.smooth_weight[pi] * g / (m * m) / ((float)q.hd[pi] * (float)q.wd[pi]);
-        }
-        __syncthreads();
-    }
-    if (tid < q.n_pass) {
-        const float photo = s_sm[0][tid], sm = s_sm[1][tid];
-        q.losses[tid * 4 + 0] = photo + q.smooth_weight[tid] * sm;   // trainer.py:610,616
-        q.losses[tid * 4 + 1] = photo;
-        q.losses[tid * 4 + 2] = sm;
-        q.losses[tid * 4 + 3] = 0.f;
-    }
-    // pose gradients: dL/dP[pass][f][b] = fixed-order sum over that image's CTAs; dL/dT = K[:3,:]^T dL/dP
-    if (q.with_grad) {
-        const int n_mat = q.n_pass * q.S * q.B;
-        for (int idx = tid; idx < n_mat * 16; idx += nt) {
-            const int e = idx & 15, mat = idx >> 4;
-            const int b = mat % q.B, f = (mat / q.B) % q.S, pi = mat / (q.B * q.S);
-            const int kk = e >> 2, j = e & 3;   // dT[k][j] = sum_i K[i][k] dP[i][j]
-            const float* Kb = q.K + (size_t)b * 16;
-            float acc = 0.f;
-            for (int i = 0; i < 3; ++i) {
-                float gp = 0.f;
-                const size_t base = (size_t)(pi * q.cta_per_pass + b * q.cta_per_image);
-                for (int c = 0; c < q.cta_per_image; ++c)
-                    gp += q.part[(base + c) * q.part_stride + 1 + f * 12 + i * 4 + j];
-                acc = fmaf(Kb[i * 4 + kk], gp, acc);
-            }
-            q.grad_T[((size_t)(pi * q.S + f) * q.B + b) * 16 + e] = acc;
+            q.grad_disp_const[pi * q.B + b] =
+                -q.smooth_weight[pi] * sg / (m * m) / ((float)q.hd[pi] * (float)q.wd[pi]);
         }
     }
+    // dL/dT = K[:3,:]^T dL/dP  (layers.py:183: P = (K T)[:3])
+    if (q.with_grad && tid < q.S * 16) {
+        const int f = tid >> 4, e = tid & 15, kk = e >> 2, j = e & 3;
+        const float* Kb = q.K + (size_t)b * 16;
+        const float* gp = s_col + 1 + f * 12;
+        q.grad_T[((size_t)(pi * q.S + f) * q.B + b) * 16 + e] =
+            fmaf(Kb[kk], gp[j], fmaf(Kb[4 + kk], gp[4 + j], Kb[8 + kk] * gp[8 + j]));
+    }
+}
+
+__global__ void __launch_bounds__(32)
+finalize_loss_kernel(const FinalizeParams q) {
+    const int pi = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    float ph = 0.f, sx = 0.f, sy = 0.f;
+    for (int b = 0; b < q.B; ++b) {
+        const float* ip = q.image_part + (size_t)(pi * q.B + b) * 4;
+        ph += ip[0]; sx += ip[1]; sy += ip[2];
+    }
+    const float h = (float)q.hd[pi], w = (float)q.wd[pi];
+    const float photo = ph * q.inv_n;
+    const float sm = sx / ((float)q.B * h * (w - 1.f)) + sy / ((float)q.B * (h - 1.f) * w);   // layers.py:215
+    q.losses[pi * 4 + 0] = photo + q.smooth_weight[pi] * sm;   // trainer.py:610,616
+    q.losses[pi * 4 + 1] = photo;
+    q.losses[pi * 4 + 2] = sm;
+    q.losses[pi * 4 + 3] = 0.f;
 }
 
 }  // namespace pml

@@ -17,27 +17,42 @@ struct SmoothParams {
     int B, n_pass;
     SmoothPass pass[PML_MAX_PASSES];
     float* disp_mean;     // [n_pass][B]
+    float* mean_part;     // [n_pass][B][max_chunks] partial sums of disp (4096 px each)
+    int max_chunks;
     float* part;          // [total_blocks][3]
 };
 
-// per-image mean of the disparity (trainer.py:612).  grid = (B, n_pass), 512 threads.
-__global__ void __launch_bounds__(512)
-disp_mean_kernel(const SmoothParams q) {
-    __shared__ float s_w[16];
-    const int b = blockIdx.x, pi = blockIdx.y;
+// per-image mean of the disparity (trainer.py:612), two stages: 4096-pixel partial sums here,
+// combined (in fixed order) by every consumer through image_mean().  grid = (chunks, B, n_pass).
+constexpr int kMeanChunk = 4096;
+__global__ void __launch_bounds__(256)
+disp_sum_kernel(const SmoothParams q) {
+    __shared__ float s_w[8];
+    const int chunk = blockIdx.x, b = blockIdx.y, pi = blockIdx.z;
     const SmoothPass& ps = q.pass[pi];
     const int n = ps.h * ps.w;
+    const int lo = chunk * kMeanChunk;
+    if (lo >= n) return;
+    const int hi = min(lo + kMeanChunk, n);
     const float* d = ps.disp + (size_t)b * n;
     float v = 0.f;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) v += __ldg(d + i);
+    for (int i = lo + threadIdx.x; i < hi; i += 256) v += __ldg(d + i);
     v = warp_sum(v);
     if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
     __syncthreads();
     if (threadIdx.x == 0) {
         float t = 0.f;
-        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_w[i];
-        q.disp_mean[pi * q.B + b] = t / (float)n;
+        for (int i = 0; i < 8; ++i) t += s_w[i];
+        q.mean_part[((size_t)pi * q.B + b) * q.max_chunks + chunk] = t;
     }
+}
+__device__ __forceinline__ float image_mean(const SmoothParams& q, int pi, int b) {
+    const SmoothPass& ps = q.pass[pi];
+    const int n = ps.h * ps.w, nc = (n + kMeanChunk - 1) / kMeanChunk;
+    const float* mp = q.mean_part + ((size_t)pi * q.B + b) * q.max_chunks;
+    float t = 0.f;
+    for (int i = 0; i < nc; ++i) t += mp[i];
+    return t / (float)n;
 }
 
 __device__ __forceinline__ float edge_weight(const float* img, size_t plane, int a, int bidx) {
@@ -51,6 +66,7 @@ template <bool GRAD>
 __global__ void __launch_bounds__(256)
 smooth_kernel(const SmoothParams q) {
     __shared__ float s_red[8][3];
+    __shared__ float s_mean;
     // locate (pass, image, block)
     int pi = 0;
 #pragma unroll 1
@@ -60,12 +76,17 @@ smooth_kernel(const SmoothParams q) {
     const int b = rel / ps.blocks, blk = rel - b * ps.blocks;
     const int h = ps.h, w = ps.w, n = h * w;
     const int idx = blk * 256 + threadIdx.x;
+    if (threadIdx.x == 0) {
+        s_mean = image_mean(q, pi, b);
+        if (blk == 0) q.disp_mean[pi * q.B + b] = s_mean;
+    }
+    __syncthreads();
     float ex = 0.f, ey = 0.f, gd = 0.f;
     if (idx < n) {
         const int y = idx / w, x = idx - y * w;
         const float* d = ps.disp + (size_t)b * n;
         const float* img = ps.color + (size_t)b * 3 * n;
-        const float inv = __fdiv_rn(1.0f, q.disp_mean[pi * q.B + b] + 1e-7f);
+        const float inv = __fdiv_rn(1.0f, s_mean + 1e-7f);
         const float nx_ = 1.0f / ((float)q.B * (float)h * (float)(w - 1));
         const float ny_ = 1.0f / ((float)q.B * (float)(h - 1) * (float)w);
         const float dc = __ldg(d + idx);
