@@ -230,7 +230,7 @@ def run_ours(args, rank, world, dev):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("photometric_kernel_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "photometric_kernel<S=%d,GRAD,SSIM>" % S, "achieved": round(achieved, 1),
+    roofline = {"bound": "hbm", "kernel": ("sweep_kernel<GRAD,SSIM> (S=%d)" if S <= 2 else "photometric_kernel<S=%d,GRAD,SSIM>") % S, "achieved": round(achieved, 1),
                 "peak": peak, "peak_source": "MEASURED_PEAKS.json (measured copy)" if peaks else "fallback 6.65 TB/s",
                 "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
                 "kernel_ms": round(kern_ms, 4), "algorithmic_bytes_per_launch": int(kern_bytes),

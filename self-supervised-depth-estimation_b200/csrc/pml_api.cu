@@ -2,6 +2,7 @@
 // plans the launch shape, carves the caller-provided workspace and enqueues kernels.
 #include "pml_common.cuh"
 #include "pml_photometric.cuh"
+#include "pml_sweep.cuh"
 #include "pml_smooth.cuh"
 #include "pml_layers.cuh"
 
@@ -17,6 +18,7 @@ constexpr int kNumSM = 148;   // B200
 inline size_t align16(size_t v) { return (v + 15) & ~size_t(15); }
 
 struct Plan {
+    bool sweep;   // warp-strip kernel (pml_sweep.cuh, S <= 2) instead of the CTA-strip kernel
     int NT, TW, TH, n_strips, n_chunks, cta_per_pass, n_cta, part_stride;
     int n_id;
     int smooth_blocks[PML_MAX_PASSES], smooth_off[PML_MAX_PASSES], smooth_total;
@@ -56,8 +58,18 @@ int validate(const pml_problem* p, bool grad) {
     return PML_OK;
 }
 
+// Which fused kernel serves this problem: the warp-strip sweep packs the two source frames of a
+// pixel into fp32x2 values (S <= 2); more source frames use the CTA-strip kernel.  PML_KERNEL=cta
+// forces the latter (A/B measurements).
+bool use_sweep(const pml_problem* p) {
+    const char* k = getenv("PML_KERNEL");
+    if (k && k[0] == 'c') return false;
+    return p->S <= 2;
+}
+
 Plan make_plan(const pml_problem* p, bool grad) {
     Plan pl;
+    pl.sweep = use_sweep(p);
     // strip width: the candidate whose strips waste the fewest columns
     int best_nt = 64;
     double best_cost = 1e30;
@@ -73,10 +85,12 @@ Plan make_plan(const pml_problem* p, bool grad) {
     if (pl.NT > 128) pl.NT = 128;
     pl.NT = (pl.NT / 32) * 32;
     pl.TW = pl.NT - 4;
+    if (pl.sweep) { pl.NT = pml::kSweepWarps * 32; pl.TW = pml::kSweepTW; }
     pl.n_strips = (p->W + pl.TW - 1) / pl.TW;
-    // strip height: the tallest chunk that still yields ~6 CTAs per SM (4 halo rows per chunk)
+    // strip height: the tallest chunk that still yields ~6 CTAs per SM (4 halo rows per chunk);
+    // warp strips: ~3 waves of 8 resident warps per SM
     int per_chunk = p->n_pass * p->B * pl.n_strips;
-    int want = (kNumSM * 6 + per_chunk - 1) / per_chunk;
+    int want = ((pl.sweep ? kNumSM * 8 * 3 : kNumSM * 6) + per_chunk - 1) / per_chunk;
     if (want < 1) want = 1;
     int th = (p->H + want - 1) / want;
     if (th < 16) th = 16;
@@ -130,6 +144,14 @@ int launch_photo(const PhotoParams& pp, int n_cta, int NT, int low_cells, cudaSt
         configured.store((int)smem, std::memory_order_relaxed);
     }
     PML_LAUNCH((photometric_kernel<S, GRAD, SSIM>), dim3(n_cta), dim3(NT), smem, st, pp);
+    return PML_OK;
+}
+
+template <bool GRAD, bool SSIM>
+int launch_sweep(const PhotoParams& pp, cudaStream_t st) {
+    const size_t smem = sweep_smem_bytes();   // < 48 KB: no opt-in needed
+    const int n_cta = (pp.n_items + kSweepWarps - 1) / kSweepWarps;
+    PML_LAUNCH((sweep_kernel<GRAD, SSIM>), dim3(n_cta), dim3(kSweepWarps * 32), smem, st, pp);
     return PML_OK;
 }
 
@@ -205,13 +227,17 @@ int run_loss(const pml_problem* p, void* ws, size_t ws_bytes, cudaStream_t st, b
         if (d.k > 1 && d.low_cols * d.low_rows > low_cells) low_cells = d.low_cols * d.low_rows;
     }
     pp.TW = pl.TW; pp.TH = pl.TH; pp.n_strips = pl.n_strips; pp.n_chunks = pl.n_chunks;
+    pp.n_items = pl.n_cta; pp.S = p->S;
     pp.cta_per_pass = pl.cta_per_pass; pp.part = part; pp.part_stride = pl.part_stride;
     pp.inv_n = (float)(1.0 / ((double)p->B * p->H * p->W));
     if (p->prof_start) pml_event_record(p->prof_start, st);
-    if (grad) rc = ssim ? dispatch_S<true, true>(p->S, pp, pl.n_cta, pl.NT, low_cells, st)
-                        : dispatch_S<true, false>(p->S, pp, pl.n_cta, pl.NT, low_cells, st);
-    else      rc = ssim ? dispatch_S<false, true>(p->S, pp, pl.n_cta, pl.NT, low_cells, st)
-                        : dispatch_S<false, false>(p->S, pp, pl.n_cta, pl.NT, low_cells, st);
+    if (pl.sweep) {
+        if (grad) rc = ssim ? launch_sweep<true, true>(pp, st) : launch_sweep<true, false>(pp, st);
+        else      rc = ssim ? launch_sweep<false, true>(pp, st) : launch_sweep<false, false>(pp, st);
+    } else if (grad) rc = ssim ? dispatch_S<true, true>(p->S, pp, pl.n_cta, pl.NT, low_cells, st)
+                               : dispatch_S<true, false>(p->S, pp, pl.n_cta, pl.NT, low_cells, st);
+    else             rc = ssim ? dispatch_S<false, true>(p->S, pp, pl.n_cta, pl.NT, low_cells, st)
+                               : dispatch_S<false, false>(p->S, pp, pl.n_cta, pl.NT, low_cells, st);
     if (rc != PML_OK) return rc;
     if (p->prof_stop) pml_event_record(p->prof_stop, st);
 

@@ -42,7 +42,9 @@ struct PhotoParams {
     const float* T[PML_MAX_SOURCES];
     const float* identity;  // [B, n_id, H, W] identity reprojection losses (automask)
     PassDev pass[PML_MAX_PASSES];
-    int TW, TH, n_strips, n_chunks, cta_per_pass;
+    int TW, TH, n_strips, n_chunks, cta_per_pass;   // cta_per_pass: work items (CTAs or warps) per pass
+    int S;            // number of source frames (run-time copy of the template parameter)
+    int n_items;      // total work items (pml_sweep.cuh: one per warp)
     float* part;      // [n_cta][part_stride]: loss partial, then S x 12 dL/dP partials
     int part_stride;
     float inv_n;      // 1 / (B*H*W)

@@ -1,0 +1,507 @@
+// Fused view-synthesis + reprojection-loss sweep, second generation ("warp strips").
+//
+// Same mathematics as pml_photometric.cuh (trainer.py:469-515 + :546-610 and their adjoint in one
+// pass; cam_points / pix_coords / warped images never exist in HBM), re-shaped around what bounds
+// this path on sm_100a: it is fp32-pipe / issue bound, not HBM bound (the 67 MB working set of the
+// headline config lives in L2), so the design minimises executed instructions and keeps every warp
+// free of block-wide barriers:
+//
+//  * one WARP owns a strip of 28 image columns (+2 halo columns each side = 32 lanes) x TH rows of
+//    one (scale, image) and marches down the rows on its own; horizontal neighbours of the 3x3 SSIM
+//    windows and of the transposed windows travel by warp shuffles -- no __syncthreads anywhere;
+//  * the two source frames of a pixel are evaluated as one packed fp32x2 value (FFMA2 on sm_100a):
+//    projection, bilinear taps, SSIM statistics, SSIM adjoint, pose / depth adjoint are written once
+//    and executed for both frames per instruction (S = 1 aliases frame 0 into the second half);
+//  * per-pixel geometry needed by the adjoint two rows later sits in a lane-private shared-memory
+//    ring (7 x 128-bit per row, conflict free), rolling 3x3 sums stay in registers;
+//  * all index arithmetic is 32 bit; the +1 taps of the bilinear gather are immediate offsets.
+//
+// Layout of the work: item = ((pass * B + b) * n_chunks + chunk) * n_strips + strip, one item per
+// warp and one warp per CTA, so that everything derived from the item (image, pass, base pointers,
+// row bounds) is provably warp-uniform and lives in uniform registers / the uniform datapath
+// instead of the 255 vector registers the rolling state needs.  Each item writes one row of
+// partials (loss, 12 x S pose-gradient sums) that finalize_image_kernel reduces in fixed order.
+#pragma once
+#include "pml_common.cuh"
+#include "pml_photometric.cuh"
+
+namespace pml {
+
+constexpr int kSweepWarps = 1;    // warps (= items) per CTA
+constexpr int kSweepTW = 28;      // owned columns per strip
+constexpr int kSweepRingQ = 7;    // float4 per lane per ring slot
+constexpr int kSweepWarpFloats = 48 + 32 + 3 * kSweepRingQ * 4 * 32;   // P/IK, staging row, ring
+
+// ---- packed fp32x2 helpers (FFMA2 / FMUL2 / FADD2 on sm_100a) -----------------------------------
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 splat(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
+__device__ __forceinline__ float2 shfl_up2(float2 v) {
+    return make_float2(__shfl_up_sync(0xffffffffu, v.x, 1), __shfl_up_sync(0xffffffffu, v.y, 1));
+}
+__device__ __forceinline__ float2 shfl_down2(float2 v) {
+    return make_float2(__shfl_down_sync(0xffffffffu, v.x, 1), __shfl_down_sync(0xffffffffu, v.y, 1));
+}
+// MUFU.RCP (1 ulp); callers add the Newton step where the quotient decides something
+__device__ __forceinline__ float rcp_approx(float x) {
+#ifdef PML_HOST_EMU
+    return 1.0f / x;
+#else
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#endif
+}
+__device__ __forceinline__ float rcp_nr(float x) {   // reciprocal, one Newton step: < 1 ulp
+    float r = rcp_approx(x);
+    return fmaf(r, fmaf(-x, r, 1.0f), r);
+}
+__device__ __forceinline__ float2 rcp_nr2(float2 x) {
+    float2 r = f2(rcp_approx(x.x), rcp_approx(x.y));
+    float2 e = fma2(f2(-x.x, -x.y), r, splat(1.0f));
+    return fma2(r, e, r);
+}
+
+// SSIM dissimilarity of one window for both frames (layers.py:238-248).  x statistics are packed
+// over the frame pair, the target statistics (my, myy + C1, sy + C2) are shared scalars.
+// If WITH_GRAD, pa / pb / pe receive d val / d(Sx, x_q-multiplier, y_q-multiplier) * 9, i.e. the
+// three adjoint coefficients of ssim_window() before the common factor kssim * wgt / 9.
+template <bool WITH_GRAD>
+__device__ __forceinline__ float2 ssim_pair(float2 Sx, float2 Sxx, float2 Sxy, float my, float myyC1, float syC2,
+                                            float2& pa, float2& pb, float2& pe) {
+    const float k9 = 1.0f / 9.0f;
+    const float2 mx = mul2(Sx, splat(k9));
+    const float2 mxx = mul2(mx, mx);
+    const float2 mxy = mul2(mx, splat(my));
+    const float2 sx = fma2(Sxx, splat(k9), f2(-mxx.x, -mxx.y));
+    const float2 sxy = fma2(Sxy, splat(k9), f2(-mxy.x, -mxy.y));
+    const float2 A1 = fma2(mxy, splat(2.0f), splat(kSsimC1));
+    const float2 A2 = fma2(sxy, splat(2.0f), splat(kSsimC2));
+    const float2 B1 = add2(mxx, splat(myyC1));
+    const float2 B2 = add2(sx, splat(syC2));
+    const float2 num = mul2(A1, A2), den = mul2(B1, B2);
+    const float2 q = f2(rcp_approx(den.x), rcp_approx(den.y));
+    // MUFU reciprocal (1 ulp) is enough here: the dissimilarity of a *warped* frame is never an
+    // exact tie (the identity candidates, which can tie exactly, come from identity_kernel)
+    const float2 ratio = mul2(num, q);
+    const float2 val = f2(__saturatef(fmaf(-0.5f, ratio.x, 0.5f)), __saturatef(fmaf(-0.5f, ratio.y, 0.5f)));
+    if (WITH_GRAD) {
+        // clamp backward passes the gradient on the closed interval: 0 <= raw <= 1  <=>  |ratio| <= 1
+        const float2 gq = f2(fabsf(ratio.x) <= 1.0f ? q.x : 0.f, fabsf(ratio.y) <= 1.0f ? q.y : 0.f);
+        pe = mul2(f2(-gq.x, -gq.y), A1);                         // d/dSxy * 9
+        pb = mul2(mul2(gq, ratio), B1);                          // 2 * d/dSxx * 9
+        const float2 w = mul2(mul2(mx, ratio), sub2(B2, B1));
+        pa = mul2(gq, fma2(splat(-my), sub2(A2, A1), w));        // d/dSx * 9
+    }
+    return val;
+}
+
+template <bool GRAD, bool SSIM>
+__global__ void __launch_bounds__(kSweepWarps * 32)
+sweep_kernel(const PhotoParams p) {
+    PML_DYN_SMEM(float, smem);
+    const int lane = threadIdx.x;
+    int wi = blockIdx.x;
+    const int item = wi;
+    const int pass_i = wi / p.cta_per_pass;
+    wi -= pass_i * p.cta_per_pass;
+    const int per_image = p.n_chunks * p.n_strips;
+    const int b = wi / per_image;
+    wi -= b * per_image;
+    const int chunk = wi / p.n_strips;
+    const int strip = wi - chunk * p.n_strips;
+    const PassDev& ps = p.pass[pass_i];
+
+    const int H = p.H, W = p.W, S = p.S;
+    const int x0 = strip * kSweepTW, x1 = min(x0 + kSweepTW, W);
+    const int y0 = chunk * p.TH, y1 = min(y0 + p.TH, H);
+    const int cx = x0 - 2 + lane;                         // column on the reflect-padded grid
+    const int rx = reflect1(clampi(cx, -1, W), W);        // image column actually evaluated
+    const bool col_in_image = (cx >= 0) && (cx < W);
+    const bool col_owned = (cx >= x0) && (cx < x1);
+    const bool lane_inner = (lane >= 1) && (lane <= 30);  // lanes whose 3x3 window is complete
+
+    const bool automask = !(p.flags & PML_FLAG_NO_AUTOMASK);
+    const bool avg = (p.flags & PML_FLAG_AVG_REPROJ) != 0;
+    const int n_id = automask ? (avg ? 1 : S) : 0;
+    const int f1 = (S > 1) ? 1 : 0;                       // frame in the second half of every pair
+
+    // ---- per-warp shared memory ----------------------------------------------------------------
+    float* wsm = smem;
+    float2* sP = reinterpret_cast<float2*>(wsm);          // [12] (frame0, frame1) of P = (K T)[:3]
+    float* sIK = wsm + 24;                                 // [9] inv_K 3x3 (+ pad to 48)
+    float* sG = wsm + 48;                                  // [32] staging row of the transposed upsample
+    float4* sRing = reinterpret_cast<float4*>(wsm + 80);   // [3][kSweepRingQ][32]
+
+    if (lane < 24) {
+        const int e = lane >> 1, f = (lane & 1) ? f1 : 0, i = e >> 2, j = e & 3;
+        const float* Kb = p.K + b * 16;
+        const float* Tb = p.T[f] + b * 16;
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a = fmaf(Kb[i * 4 + k], Tb[k * 4 + j], a);   // layers.py:183
+        wsm[lane] = a;
+    }
+    if (lane < 9) sIK[lane] = p.invK[b * 16 + (lane / 3) * 4 + (lane % 3)];      // layers.py:164
+    __syncwarp();
+
+    float2 P[12];
+#pragma unroll
+    for (int e = 0; e < 12; ++e) P[e] = sP[e];
+    const float ik1 = sIK[1], ik2 = sIK[2], ik4 = sIK[4], ik5 = sIK[5], ik7 = sIK[7], ik8 = sIK[8];
+    const float fxc = (float)rx;
+    const float rc0 = sIK[0] * fxc, rc1 = sIK[3] * fxc, rc2 = sIK[6] * fxc;
+
+    // horizontal part of the disparity upsample (trainer.py:474): fixed per lane
+    const int kk = ps.k, wd = ps.wd, hd = ps.hd;
+    int j0 = rx, j1 = rx;
+    float lam = 0.f;
+    if (kk > 1) {
+        const float sx = fmaxf(fmaf(ps.rscale, (float)rx + 0.5f, -0.5f), 0.f);
+        j0 = (int)sx;
+        j1 = min(j0 + 1, wd - 1);
+        lam = sx - (float)j0;
+    }
+
+    const int plane = H * W;
+    const float* tgt_b = p.target + (size_t)b * 3 * plane;
+    const float* src0_b = p.src[0] + (size_t)b * 3 * plane;
+    const float* src1_b = p.src[f1] + (size_t)b * 3 * plane;
+    const float* disp_b = ps.disp + (size_t)b * hd * wd;
+    const float* id_b = p.identity + (size_t)b * n_id * plane;
+    const float* nz_b = (ps.noise != nullptr) ? ps.noise + (size_t)b * n_id * plane : nullptr;
+    const float wscale = (float)W / (float)(W - 1), hscale = (float)H / (float)(H - 1);
+    const float wmax = (float)(W - 1), hmax = (float)(H - 1);
+    const float wmax1 = (float)(W - 2), hmax1 = (float)(H - 2);
+
+    // ---- rolling state ---------------------------------------------------------------------------
+    float hy1[3], hy2[3], hyy1[3], hyy2[3];
+    float2 hx1[3], hx2[3], hxx1[3], hxx2[3], hxy1[3], hxy2[3];
+    float2 hc1[GRAD ? 9 : 1], hc2[GRAD ? 9 : 1];
+    float2 gP[GRAD ? 12 : 1];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        hy1[c] = hy2[c] = hyy1[c] = hyy2[c] = 0.f;
+        hx1[c] = hx2[c] = hxx1[c] = hxx2[c] = hxy1[c] = hxy2[c] = splat(0.f);
+    }
+#pragma unroll
+    for (int m = 0; m < (GRAD ? 9 : 1); ++m) hc1[m] = hc2[m] = splat(0.f);
+#pragma unroll
+    for (int e = 0; e < (GRAD ? 12 : 1); ++e) gP[e] = splat(0.f);
+    float loss_acc = 0.f;
+    float2 l1_prev = splat(0.f);     // sum_c |target - pred| of the previous row
+    float2 wq_prev = splat(0.f);     // winner weight / N of the previous window row
+    // transposed vertical upsample: low-res rows `cur` and `cur + 1` accumulate in registers
+    float acc0 = 0.f, acc1 = 0.f;
+    int cur = 0, jbase = 0;
+    if (GRAD && kk > 1) {
+        cur = (int)fmaxf(fmaf(ps.rscale, (float)y0 + 0.5f, -0.5f), 0.f);
+        jbase = (int)fmaxf(fmaf(ps.rscale, (float)x0 + 0.5f, -0.5f), 0.f);
+    }
+    const int low_cols = kSweepTW / kk + 3;
+
+    const float wl = (cx == 1) ? 2.f : 1.f, wr = (cx == W - 2) ? 2.f : 1.f;   // reflection fold (columns)
+    const float kssim9 = SSIM ? (0.85f / 27.0f) : 0.f;      // 0.85 / 3 channels / 9 window taps
+    const float kl1 = SSIM ? (0.15f / 3.0f) : (1.0f / 3.0f);
+
+    // transposed horizontal upsample of one finished low-res row, added to grad_disp
+    auto flush_row = [&](int irow, float h) {
+        sG[lane] = h;
+        __syncwarp();
+        const int j = jbase + lane;
+        if (lane < low_cols && j < wd) {
+            const int xa = max(kk * j - kk / 2, x0), xb = min(kk * j + (3 * kk) / 2 - 1, x1 - 1);
+            float s = 0.f;
+            for (int x = xa; x <= xb; ++x) {
+                const float sx = fmaxf(fmaf(ps.rscale, (float)x + 0.5f, -0.5f), 0.f);
+                const int jj0 = (int)sx, jj1 = min(jj0 + 1, wd - 1);
+                const float l = sx - (float)jj0;
+                const float w = (jj0 == j ? 1.f - l : 0.f) + (jj1 == j ? l : 0.f);
+                s = fmaf(w, sG[x - x0 + 2], s);
+            }
+            if (s != 0.f) atomicAdd(ps.grad_disp + (size_t)b * hd * wd + irow * wd + j, s);
+        }
+        __syncwarp();
+    };
+
+    int slotA = 0;   // ring slot of row r; (slotA+2)%3 holds row r-1, (slotA+1)%3 row r-2
+    const int r_end = GRAD ? (y1 + 1) : y1;
+#pragma unroll 1
+    for (int r = y0 - 2; r <= r_end; ++r) {
+        // =================================== (A) warp row r ======================================
+        const int ry = reflect1(clampi(r, -1, H), H);
+        const int offy = ry * W + rx;
+        float yv[3];
+#pragma unroll
+        {
+            const float* tq = tgt_b + offy;
+            yv[0] = __ldg(tq); yv[1] = __ldg(tq + plane); yv[2] = __ldg(tq + 2 * plane);
+        }
+        float d;
+        if (kk > 1) {   // bilinear upsample of disp_s, align_corners=False (trainer.py:474)
+            const float sy = fmaxf(fmaf(ps.rscale, (float)ry + 0.5f, -0.5f), 0.f);
+            const int i0 = (int)sy, i1 = min(i0 + 1, hd - 1);
+            const float mu = sy - (float)i0;
+            const float v00 = __ldg(disp_b + i0 * wd + j0), v01 = __ldg(disp_b + i0 * wd + j1);
+            const float v10 = __ldg(disp_b + i1 * wd + j0), v11 = __ldg(disp_b + i1 * wd + j1);
+            const float top = fmaf(lam, v01, (1.f - lam) * v00), bot = fmaf(lam, v11, (1.f - lam) * v10);
+            d = fmaf(mu, bot, (1.f - mu) * top);
+        } else {
+            d = __ldg(disp_b + offy);
+        }
+        const float sigma = fmaf(p.disp_range, d, p.min_disp);   // layers.py:23
+        const float D = rcp_nr(sigma);                            // layers.py:24
+        const float fy = (float)ry;
+        const float r0 = rc0 + fmaf(ik1, fy, ik2);
+        const float r1 = rc1 + fmaf(ik4, fy, ik5);
+        const float r2 = rc2 + fmaf(ik7, fy, ik8);
+        const float X0 = D * r0, X1 = D * r1, X2 = D * r2;       // layers.py:165
+        const bool emit = col_owned && (r >= y0) && (r < y1);
+        if (ps.depth != nullptr && emit) ps.depth[(size_t)b * plane + r * W + cx] = D;
+
+        // projection of both frames (layers.py:183-187)
+        const float2 c0 = fma2(P[0], splat(X0), fma2(P[1], splat(X1), fma2(P[2], splat(X2), P[3])));
+        const float2 c1 = fma2(P[4], splat(X0), fma2(P[5], splat(X1), fma2(P[6], splat(X2), P[7])));
+        const float2 c2 = fma2(P[8], splat(X0), fma2(P[9], splat(X1), fma2(P[10], splat(X2), P[11])));
+        const float2 invz = rcp_nr2(add2(c2, splat(p.eps)));
+        const float2 u = mul2(c0, invz), v = mul2(c1, invz);
+        // layers.py:190-192 + grid_sample unnormalise (align_corners=False): ix = u*W/(W-1) - 0.5
+        const float2 ixr = fma2(u, splat(wscale), splat(-0.5f)), iyr = fma2(v, splat(hscale), splat(-0.5f));
+        const float2 ix = f2(fminf(fmaxf(ixr.x, 0.f), wmax), fminf(fmaxf(ixr.y, 0.f), wmax));
+        const float2 iy = f2(fminf(fmaxf(iyr.x, 0.f), hmax), fminf(fmaxf(iyr.y, 0.f), hmax));
+        // base tap clamped to W-2 / H-2: the +1 tap then always exists and carries the weight that
+        // grid_sample gives to the last column / row (its out-of-range tap has weight 0)
+        const float2 fx0 = f2(fminf(floorf(ix.x), wmax1), fminf(floorf(ix.y), wmax1));
+        const float2 fy0 = f2(fminf(floorf(iy.x), hmax1), fminf(floorf(iy.y), hmax1));
+        const float2 tx = sub2(ix, fx0), ty = sub2(iy, fy0);
+        // clip backward (zero outside the open interval) times d ix / d u
+        const float2 mx = f2((ixr.x > 0.f && ixr.x < wmax) ? wscale : 0.f, (ixr.y > 0.f && ixr.y < wmax) ? wscale : 0.f);
+        const float2 my = f2((iyr.x > 0.f && iyr.x < hmax) ? hscale : 0.f, (iyr.y > 0.f && iyr.y < hmax) ? hscale : 0.f);
+        const int o0 = (int)fy0.x * W + (int)fx0.x, o1 = (int)fy0.y * W + (int)fx0.y;
+
+        float2 xv[3], dpx[3], dpy[3];
+        float2 l1_cur = splat(0.f);
+        const float* q0 = src0_b + o0;    // one 64-bit address per frame; every other tap is a
+        const float* q1 = src1_b + o1;    // warp-uniform offset (plane, W) or the immediate +1
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int oc = c * plane, ocw = c * plane + W;
+            const float2 nw = f2(__ldg(q0 + oc), __ldg(q1 + oc)), ne = f2(__ldg(q0 + oc + 1), __ldg(q1 + oc + 1));
+            const float2 sw = f2(__ldg(q0 + ocw), __ldg(q1 + ocw)), se = f2(__ldg(q0 + ocw + 1), __ldg(q1 + ocw + 1));
+            const float2 dt = sub2(ne, nw), db = sub2(se, sw);
+            const float2 top = fma2(tx, dt, nw), bot = fma2(tx, db, sw);
+            const float2 dvert = sub2(bot, top);
+            xv[c] = fma2(ty, dvert, top);
+            if (GRAD) {
+                dpx[c] = mul2(mx, fma2(ty, sub2(db, dt), dt));
+                dpy[c] = mul2(my, dvert);
+            }
+            const float2 df = sub2(xv[c], splat(yv[c]));
+            l1_cur.x += fabsf(df.x);
+            l1_cur.y += fabsf(df.y);
+            if (ps.warped != nullptr && emit) {
+                ps.warped[((size_t)(0 * p.B + b) * 3 + c) * plane + r * W + cx] = xv[c].x;
+                if (S > 1) ps.warped[((size_t)(1 * p.B + b) * 3 + c) * plane + r * W + cx] = xv[c].y;
+            }
+        }
+        if (GRAD) {
+            float4* ra = sRing + (slotA * kSweepRingQ) * 32 + lane;
+            ra[0 * 32] = make_float4(yv[0], yv[1], yv[2], D);
+            ra[1 * 32] = make_float4(xv[0].x, xv[0].y, xv[1].x, xv[1].y);
+            ra[2 * 32] = make_float4(xv[2].x, xv[2].y, dpx[0].x, dpx[0].y);
+            ra[3 * 32] = make_float4(dpx[1].x, dpx[1].y, dpx[2].x, dpx[2].y);
+            ra[4 * 32] = make_float4(dpy[0].x, dpy[0].y, dpy[1].x, dpy[1].y);
+            ra[5 * 32] = make_float4(dpy[2].x, dpy[2].y, invz.x, invz.y);
+            ra[6 * 32] = make_float4(u.x, u.y, v.x, v.y);
+        }
+
+        // ========================= (B) close the windows centred on row r-1 ======================
+        const int py = r - 1;
+        const bool p_valid = (r >= y0) && (py >= 0) && (py < H) && col_in_image && lane_inner;
+        float2 rp = splat(0.f);
+        float2 pa[3], pb[3], pe[3];
+        {
+            float2 ssim_sum = splat(0.f);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                if (SSIM) {
+                    const float yl = __shfl_up_sync(0xffffffffu, yv[c], 1), yr = __shfl_down_sync(0xffffffffu, yv[c], 1);
+                    const float hyn = yl + yv[c] + yr;
+                    const float hyyn = fmaf(yl, yl, fmaf(yv[c], yv[c], yr * yr));
+                    const float2 xl = shfl_up2(xv[c]), xr = shfl_down2(xv[c]);
+                    const float2 hxn = add2(add2(xl, xv[c]), xr);
+                    const float2 hxxn = fma2(xl, xl, fma2(xv[c], xv[c], mul2(xr, xr)));
+                    const float2 hxyn = fma2(xl, splat(yl), fma2(xv[c], splat(yv[c]), mul2(xr, splat(yr))));
+                    const float Sy = hy2[c] + hy1[c] + hyn;
+                    const float Syy = hyy2[c] + hyy1[c] + hyyn;
+                    const float2 Sx = add2(add2(hx2[c], hx1[c]), hxn);
+                    const float2 Sxx = add2(add2(hxx2[c], hxx1[c]), hxxn);
+                    const float2 Sxy = add2(add2(hxy2[c], hxy1[c]), hxyn);
+                    hy2[c] = hy1[c]; hy1[c] = hyn; hyy2[c] = hyy1[c]; hyy1[c] = hyyn;
+                    hx2[c] = hx1[c]; hx1[c] = hxn; hxx2[c] = hxx1[c]; hxx1[c] = hxxn;
+                    hxy2[c] = hxy1[c]; hxy1[c] = hxyn;
+                    const float k9 = 1.0f / 9.0f;
+                    const float my_ = Sy * k9;
+                    const float myy = my_ * my_;
+                    const float sy_ = fmaf(Syy, k9, -myy);
+                    ssim_sum = add2(ssim_sum, ssim_pair<GRAD>(Sx, Sxx, Sxy, my_, myy + kSsimC1, sy_ + kSsimC2,
+                                                              pa[c], pb[c], pe[c]));
+                }
+            }
+            // trainer.py:527 (0.85 * SSIM.mean(1) + 0.15 * L1.mean(1)) or :523 (L1 only)
+            rp = SSIM ? fma2(ssim_sum, splat(0.85f / 3.0f), mul2(l1_prev, splat(0.15f / 3.0f)))
+                      : mul2(l1_prev, splat(1.0f / 3.0f));
+        }
+        l1_prev = l1_cur;
+
+        float2 wgt = splat(0.f);
+        if (p_valid) {
+            // candidates in the reference's order: identity (+noise) first, then reprojection
+            // (trainer.py:597); torch.min returns the first minimum.
+            float best = 3.0e38f;
+            int best_i = 0;
+            const int pix = py * W + cx;
+            if (n_id > 0) {
+                float nz0, nz1 = 0.f;
+                if (nz_b != nullptr) {
+                    nz0 = __ldg(nz_b + pix);
+                    if (n_id > 1) nz1 = __ldg(nz_b + pix + plane);
+                } else {
+                    float nz[4];
+                    const size_t lin = (size_t)b * plane + pix;
+                    philox_normal4(p.seed, (uint32_t)lin, (uint32_t)(lin >> 32), (uint32_t)pass_i, nz);
+                    nz0 = nz[0]; nz1 = nz[1];
+                }
+                best = fmaf(nz0, kTieNoise, __ldg(id_b + pix));
+                if (n_id > 1) {
+                    const float cand = fmaf(nz1, kTieNoise, __ldg(id_b + pix + plane));
+                    if (cand < best) { best = cand; best_i = 1; }
+                }
+            }
+            if (avg) {
+                const float m = (S > 1) ? (rp.x + rp.y) / 2.0f : rp.x;
+                if (m < best) { best = m; best_i = n_id; }
+                if (best_i == n_id) wgt = (S > 1) ? splat(0.5f) : f2(1.f, 0.f);
+            } else {
+                if (rp.x < best) { best = rp.x; best_i = n_id; }
+                if (S > 1 && rp.y < best) { best = rp.y; best_i = n_id + 1; }
+                wgt = f2(best_i == n_id ? 1.f : 0.f, best_i == n_id + 1 ? 1.f : 0.f);
+            }
+            if (col_owned && py >= y0 && py < y1) {
+                loss_acc += best;
+                if (ps.argmin != nullptr) ps.argmin[(size_t)b * plane + pix] = (uint8_t)best_i;
+            }
+        }
+
+        // ========================= (C) adjoint for the pixels of row r-2 =========================
+        if (GRAD) {
+            const float2 wsc = mul2(wgt, splat(p.inv_n));      // winner weight of window row r-1
+            const int qy = r - 2;
+            const bool do_q = (r >= y0 + 2);                   // => y0 <= qy < y1
+            const float wt = (qy == 1) ? 2.f : 1.f, wb = (qy == H - 2) ? 2.f : 1.f;   // reflection fold (rows)
+            float2 V[9];
+            if (SSIM) {
+                const float2 base = mul2(wsc, splat(kssim9));
+#pragma unroll
+                for (int m = 0; m < 9; ++m) {
+                    const int c = m % 3;
+                    // d rp / d x_q = (0.85/27) * (pa + x_q pb + y_q pe) for q in the window of p
+                    const float2 cf = mul2(base, m < 3 ? pa[c] : (m < 6 ? pb[c] : pe[c]));
+                    const float2 cl = shfl_up2(cf), cr = shfl_down2(cf);
+                    const float2 hn = fma2(splat(wl), cl, fma2(splat(wr), cr, cf));
+                    V[m] = fma2(splat(wt), hc2[m], fma2(splat(wb), hn, hc1[m]));
+                    hc2[m] = hc1[m];
+                    hc1[m] = hn;
+                }
+            }
+            float g_d = 0.f;
+            if (do_q && col_owned) {
+                const float4* rc = sRing + (((slotA + 1) % 3) * kSweepRingQ) * 32 + lane;
+                const float4 q0 = rc[0 * 32], q1 = rc[1 * 32], q2 = rc[2 * 32], q3 = rc[3 * 32];
+                const float4 q4 = rc[4 * 32], q5 = rc[5 * 32], q6 = rc[6 * 32];
+                const float yq[3] = {q0.x, q0.y, q0.z};
+                const float Dq = q0.w;
+                const float2 xq[3] = {f2(q1.x, q1.y), f2(q1.z, q1.w), f2(q2.x, q2.y)};
+                const float2 dxq[3] = {f2(q2.z, q2.w), f2(q3.x, q3.y), f2(q3.z, q3.w)};
+                const float2 dyq[3] = {f2(q4.x, q4.y), f2(q4.z, q4.w), f2(q5.x, q5.y)};
+                const float2 invzq = f2(q5.z, q5.w), uq = f2(q6.x, q6.y), vq = f2(q6.z, q6.w);
+                const float2 kw = mul2(wq_prev, splat(kl1));   // wq_prev: winner weight of row r-2
+                float2 du = splat(0.f), dv = splat(0.f);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float2 df = sub2(xq[c], splat(yq[c]));
+                    // d|x - y| / dx = sign(x - y).  sign(0) is taken as +1 instead of the reference's 0:
+                    // exact equality of a warped value and the target only happens on locally constant
+                    // images, where the bilinear slopes that multiply this term are exactly 0
+                    const float2 sg = f2(copysignf(kw.x, df.x), copysignf(kw.y, df.y));
+                    float2 g = sg;
+                    if (SSIM) g = add2(g, fma2(xq[c], V[3 + c], fma2(splat(yq[c]), V[6 + c], V[c])));
+                    du = fma2(g, dxq[c], du);
+                    dv = fma2(g, dyq[c], dv);
+                }
+                const float2 dc0 = mul2(du, invzq), dc1 = mul2(dv, invzq);
+                const float2 t = fma2(uq, du, mul2(vq, dv));
+                const float2 dc2 = mul2(f2(-t.x, -t.y), invzq);
+                const float fq = (float)qy;
+                const float rq0 = rc0 + fmaf(ik1, fq, ik2), rq1 = rc1 + fmaf(ik4, fq, ik5), rq2 = rc2 + fmaf(ik7, fq, ik8);
+                const float Xq0 = Dq * rq0, Xq1 = Dq * rq1, Xq2 = Dq * rq2;
+                gP[0] = fma2(dc0, splat(Xq0), gP[0]); gP[1] = fma2(dc0, splat(Xq1), gP[1]);
+                gP[2] = fma2(dc0, splat(Xq2), gP[2]); gP[3] = add2(gP[3], dc0);
+                gP[4] = fma2(dc1, splat(Xq0), gP[4]); gP[5] = fma2(dc1, splat(Xq1), gP[5]);
+                gP[6] = fma2(dc1, splat(Xq2), gP[6]); gP[7] = add2(gP[7], dc1);
+                gP[8] = fma2(dc2, splat(Xq0), gP[8]); gP[9] = fma2(dc2, splat(Xq1), gP[9]);
+                gP[10] = fma2(dc2, splat(Xq2), gP[10]); gP[11] = add2(gP[11], dc2);
+                const float2 gX0 = fma2(P[0], dc0, fma2(P[4], dc1, mul2(P[8], dc2)));
+                const float2 gX1 = fma2(P[1], dc0, fma2(P[5], dc1, mul2(P[9], dc2)));
+                const float2 gX2 = fma2(P[2], dc0, fma2(P[6], dc1, mul2(P[10], dc2)));
+                const float2 gD = fma2(splat(rq0), gX0, fma2(splat(rq1), gX1, mul2(splat(rq2), gX2)));
+                g_d = -p.disp_range * Dq * Dq * (gD.x + gD.y);   // d(1/sigma)/d disp, both frames
+            }
+            wq_prev = wsc;
+            if (do_q) {
+                if (kk > 1) {
+                    const float sy = fmaxf(fmaf(ps.rscale, (float)qy + 0.5f, -0.5f), 0.f);
+                    const int i0 = (int)sy;
+                    const float mu = sy - (float)i0;
+                    if (i0 > cur) {            // low-res row `cur` is complete (warp-uniform)
+                        flush_row(cur, acc0);
+                        acc0 = acc1; acc1 = 0.f; cur = i0;
+                    }
+                    if (i0 + 1 <= hd - 1) { acc0 = fmaf(1.f - mu, g_d, acc0); acc1 = fmaf(mu, g_d, acc1); }
+                    else acc0 += g_d;
+                } else if (col_owned && ps.grad_disp != nullptr) {
+                    ps.grad_disp[(size_t)b * plane + qy * W + cx] += g_d;
+                }
+            }
+        }
+        slotA = (slotA + 1 == 3) ? 0 : slotA + 1;
+    }
+
+    // ------------------------------------ epilogue ------------------------------------------------
+    if (GRAD && kk > 1) {
+        flush_row(cur, acc0);
+        if (cur + 1 <= hd - 1) flush_row(cur + 1, acc1);
+    }
+    float* out = p.part + (size_t)item * p.part_stride;
+    {
+        const float v = warp_sum(loss_acc);
+        if (lane == 0) out[0] = v;
+    }
+    if (GRAD) {
+#pragma unroll
+        for (int e = 0; e < 12; ++e) {
+            const float a = warp_sum(gP[e].x), c = warp_sum(gP[e].y);
+            if (lane == 0) {
+                out[1 + e] = a;
+                if (S > 1) out[1 + 12 + e] = c;
+            }
+        }
+    }
+}
+
+inline size_t sweep_smem_bytes() { return (size_t)kSweepWarps * kSweepWarpFloats * sizeof(float) + 16; }
+
+}  // namespace pml

@@ -119,6 +119,11 @@ template <class T> static inline T __shfl_down_sync(unsigned, T v, int d) {
     T r = emu_shfl(v, lane + d);
     return (lane + d < 32) ? r : v;
 }
+template <class T> static inline T __shfl_up_sync(unsigned, T v, int d) {
+    unsigned lane = emu::linear_tid() % 32;
+    T r = emu_shfl(v, lane >= (unsigned)d ? lane - d : lane);
+    return r;
+}
 template <class T> static inline T __shfl_sync(unsigned, T v, int l) { return emu_shfl(v, (unsigned)l); }
 
 static inline float atomicAdd(float* p, float v) { return std::atomic_ref<float>(*p).fetch_add(v); }
@@ -128,6 +133,9 @@ static inline int atomicAdd(int* p, int v) { return std::atomic_ref<int>(*p).fet
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return float2{std::fmaf(a.x, b.x, c.x), std::fmaf(a.y, b.y, c.y)}; }
+static inline float2 __fmul2_rn(float2 a, float2 b) { return float2{a.x * b.x, a.y * b.y}; }
+static inline float2 __fadd2_rn(float2 a, float2 b) { return float2{a.x + b.x, a.y + b.y}; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __frcp_rn(float a) { return 1.0f / a; }
 static inline float __fdiv_rn(float a, float b) { return a / b; }
