@@ -105,4 +105,26 @@ __device__ __forceinline__ void philox_normal4(uint64_t seed, uint32_t idx_lo, u
     }
 }
 
+
+// Philox2x32-10 -> two standard normals by one Box-Muller step: the tie-break noise of one pixel
+// (two identity candidates, trainer.py:594) from ~45 instructions.  The noise only orders candidates
+// that are closer than ~1e-4, so MUFU-precision log / sin / cos are ample.
+__device__ __forceinline__ void philox2_normal2(uint32_t key, uint32_t c0, uint32_t c1, float& n0, float& n1) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi = __umulhi(0xD256D193u, c0), lo = 0xD256D193u * c0;
+        c0 = hi ^ key ^ c1;
+        c1 = lo;
+        key += 0x9E3779B9u;
+    }
+    const float k = 2.3283064365386963e-10f;            // 2^-32
+    const float u1 = ((float)c0 + 1.0f) * k;            // (0,1]
+    const float ang = ((float)c1 * k - 0.5f) * 6.283185307179586f;   // [-pi, pi)
+    const float rad = sqrtf(-2.0f * __logf(u1));
+    float sn, cs;
+    __sincosf(ang, &sn, &cs);
+    n0 = rad * cs;
+    n1 = rad * sn;
+}
+
 }  // namespace pml

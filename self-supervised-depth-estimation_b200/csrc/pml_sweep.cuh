@@ -45,6 +45,14 @@ __device__ __forceinline__ float2 shfl_up2(float2 v) {
 __device__ __forceinline__ float2 shfl_down2(float2 v) {
     return make_float2(__shfl_down_sync(0xffffffffu, v.x, 1), __shfl_down_sync(0xffffffffu, v.y, 1));
 }
+// L1 prefetch of one line (CCTL.E.PF1): no destination register, never waited on
+__device__ __forceinline__ void prefetch_l1(const void* ptr) {
+#ifndef PML_HOST_EMU
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
+#else
+    (void)ptr;
+#endif
+}
 // MUFU.RCP (1 ulp); callers add the Newton step where the quotient decides something
 __device__ __forceinline__ float rcp_approx(float x) {
 #ifdef PML_HOST_EMU
@@ -99,20 +107,41 @@ __device__ __forceinline__ float2 ssim_pair(float2 Sx, float2 Sxx, float2 Sxy, f
     return val;
 }
 
-template <bool GRAD, bool SSIM>
+// Transposed horizontal upsample of one finished low-res row of disparity gradients (the adjoint
+// of trainer.py:474 along x), added to grad_disp.  `h` holds this lane's full-res column sum (0 for
+// halo lanes); low-res column jbase + lane collects the <= 2k full-res columns that touch it.
+// Runs once per k rows and strip, hence out of line.
+__device__ __noinline__ void sweep_flush_row(float* sG, float* gd_row, float h, int lane, int jbase, int low_cols,
+                                             int wd, int kk, int x0, int x1, float rscale) {
+    sG[lane] = h;
+    __syncwarp();
+    const int j = jbase + lane;
+    if (lane < low_cols && j < wd) {
+        const int xa = max(kk * j - kk / 2, x0), xb = min(kk * j + (3 * kk) / 2 - 1, x1 - 1);
+        float s = 0.f;
+        for (int x = xa; x <= xb; ++x) {
+            const float sx = fmaxf(fmaf(rscale, (float)x + 0.5f, -0.5f), 0.f);
+            const int jj0 = (int)sx, jj1 = min(jj0 + 1, wd - 1);
+            const float l = sx - (float)jj0;
+            const float w = (jj0 == j ? 1.f - l : 0.f) + (jj1 == j ? l : 0.f);
+            s = fmaf(w, sG[x - x0 + 2], s);
+        }
+        if (s != 0.f) atomicAdd(gd_row + j, s);
+    }
+    __syncwarp();
+}
+
+template <bool GRAD, bool SSIM, bool PREFETCH>
 __global__ void __launch_bounds__(kSweepWarps * 32)
 sweep_kernel(const PhotoParams p) {
     PML_DYN_SMEM(float, smem);
+    // grid = (n_chunks * n_strips, B, n_pass): image and pass come straight from blockIdx, so every
+    // base pointer derived from them is warp-uniform by construction (no division on that path)
     const int lane = threadIdx.x;
-    int wi = blockIdx.x;
-    const int item = wi;
-    const int pass_i = wi / p.cta_per_pass;
-    wi -= pass_i * p.cta_per_pass;
-    const int per_image = p.n_chunks * p.n_strips;
-    const int b = wi / per_image;
-    wi -= b * per_image;
-    const int chunk = wi / p.n_strips;
-    const int strip = wi - chunk * p.n_strips;
+    const int b = blockIdx.y, pass_i = blockIdx.z;
+    const int chunk = blockIdx.x / p.n_strips;
+    const int strip = blockIdx.x - chunk * p.n_strips;
+    const int item = (pass_i * p.B + b) * (p.n_chunks * p.n_strips) + blockIdx.x;
     const PassDev& ps = p.pass[pass_i];
 
     const int H = p.H, W = p.W, S = p.S;
@@ -167,12 +196,18 @@ sweep_kernel(const PhotoParams p) {
     }
 
     const int plane = H * W;
-    const float* tgt_b = p.target + (size_t)b * 3 * plane;
-    const float* src0_b = p.src[0] + (size_t)b * 3 * plane;
-    const float* src1_b = p.src[f1] + (size_t)b * 3 * plane;
-    const float* disp_b = ps.disp + (size_t)b * hd * wd;
-    const float* id_b = p.identity + (size_t)b * n_id * plane;
-    const float* nz_b = (ps.noise != nullptr) ? ps.noise + (size_t)b * n_id * plane : nullptr;
+    // All global addressing is `parameter pointer [32-bit element index]` (one IMAD.WIDE per address):
+    // every tensor of a call has < 2^31 elements (checked on the host).
+    const float* __restrict__ tgt_g = p.target;
+    const float* __restrict__ src0_g = p.src[0];
+    const float* __restrict__ src1_g = p.src[f1];
+    const float* __restrict__ disp_g = ps.disp;
+    const float* __restrict__ id_g = p.identity;
+    const float* __restrict__ nz_g = ps.noise;
+    const int b3p = b * 3 * plane;          // image offset in a [B,3,H,W] tensor
+    const int bdp = b * hd * wd;            // ... in disp_s / grad_disp_s
+    const int bip = b * n_id * plane;       // ... in the identity-loss / noise tensors
+    const int bp = b * plane;               // ... in a [B,1,H,W] tensor
     const float wscale = (float)W / (float)(W - 1), hscale = (float)H / (float)(H - 1);
     const float wmax = (float)(W - 1), hmax = (float)(H - 1);
     const float wmax1 = (float)(W - 2), hmax1 = (float)(H - 2);
@@ -207,50 +242,55 @@ sweep_kernel(const PhotoParams p) {
     const float kssim9 = SSIM ? (0.85f / 27.0f) : 0.f;      // 0.85 / 3 channels / 9 window taps
     const float kl1 = SSIM ? (0.15f / 3.0f) : (1.0f / 3.0f);
 
-    // transposed horizontal upsample of one finished low-res row, added to grad_disp
     auto flush_row = [&](int irow, float h) {
-        sG[lane] = h;
-        __syncwarp();
-        const int j = jbase + lane;
-        if (lane < low_cols && j < wd) {
-            const int xa = max(kk * j - kk / 2, x0), xb = min(kk * j + (3 * kk) / 2 - 1, x1 - 1);
-            float s = 0.f;
-            for (int x = xa; x <= xb; ++x) {
-                const float sx = fmaxf(fmaf(ps.rscale, (float)x + 0.5f, -0.5f), 0.f);
-                const int jj0 = (int)sx, jj1 = min(jj0 + 1, wd - 1);
-                const float l = sx - (float)jj0;
-                const float w = (jj0 == j ? 1.f - l : 0.f) + (jj1 == j ? l : 0.f);
-                s = fmaf(w, sG[x - x0 + 2], s);
-            }
-            if (s != 0.f) atomicAdd(ps.grad_disp + (size_t)b * hd * wd + irow * wd + j, s);
-        }
-        __syncwarp();
+        sweep_flush_row(sG, ps.grad_disp + (bdp + irow * wd), h, lane, jbase, low_cols, wd, kk, x0, x1,
+                        ps.rscale);
     };
 
     int slotA = 0;   // ring slot of row r; (slotA+2)%3 holds row r-1, (slotA+1)%3 row r-2
     const int r_end = GRAD ? (y1 + 1) : y1;
-#pragma unroll 1
-    for (int r = y0 - 2; r <= r_end; ++r) {
+    // One row step.  The rolling 3x3 sums are passed as (previous row, row before): the step reads
+    // both and overwrites the older one, so calling it with the two sets swapped on alternate rows
+    // (loop unrolled by two below) rotates the window without a single register move.
+    auto step = [&](const int r, float (&hyA)[3], float (&hyB)[3], float (&hyyA)[3], float (&hyyB)[3],
+                    float2 (&hxA)[3], float2 (&hxB)[3], float2 (&hxxA)[3], float2 (&hxxB)[3],
+                    float2 (&hxyA)[3], float2 (&hxyB)[3], float2 (&hcA)[GRAD ? 9 : 1], float2 (&hcB)[GRAD ? 9 : 1]) {
         // =================================== (A) warp row r ======================================
         const int ry = reflect1(clampi(r, -1, H), H);
         const int offy = ry * W + rx;
         float yv[3];
-#pragma unroll
         {
-            const float* tq = tgt_b + offy;
-            yv[0] = __ldg(tq); yv[1] = __ldg(tq + plane); yv[2] = __ldg(tq + 2 * plane);
+            const int ty_ = b3p + offy;
+            yv[0] = __ldg(tgt_g + ty_); yv[1] = __ldg(tgt_g + ty_ + plane); yv[2] = __ldg(tgt_g + ty_ + 2 * plane);
+            if (PREFETCH) {
+                // streaming inputs of the next row step: target row r+1, identity / noise of window row r
+                const int rn = reflect1(clampi(r + 1, -1, H), H) - ry;   // -1, 0 or +1 rows
+                const int tn = ty_ + rn * W;
+                prefetch_l1(tgt_g + tn); prefetch_l1(tgt_g + tn + plane); prefetch_l1(tgt_g + tn + 2 * plane);
+                if (kk == 1) prefetch_l1(disp_g + bdp + offy + rn * W);
+                if (n_id > 0) {
+                    const int pr = bip + clampi(r, 0, H - 1) * W + rx;
+                    prefetch_l1(id_g + pr);
+                    if (nz_g != nullptr) prefetch_l1(nz_g + pr);
+                    if (n_id > 1) {
+                        prefetch_l1(id_g + pr + plane);
+                        if (nz_g != nullptr) prefetch_l1(nz_g + pr + plane);
+                    }
+                }
+            }
         }
         float d;
         if (kk > 1) {   // bilinear upsample of disp_s, align_corners=False (trainer.py:474)
             const float sy = fmaxf(fmaf(ps.rscale, (float)ry + 0.5f, -0.5f), 0.f);
             const int i0 = (int)sy, i1 = min(i0 + 1, hd - 1);
             const float mu = sy - (float)i0;
-            const float v00 = __ldg(disp_b + i0 * wd + j0), v01 = __ldg(disp_b + i0 * wd + j1);
-            const float v10 = __ldg(disp_b + i1 * wd + j0), v11 = __ldg(disp_b + i1 * wd + j1);
+            const int a0 = bdp + i0 * wd, a1 = bdp + i1 * wd;
+            const float v00 = __ldg(disp_g + a0 + j0), v01 = __ldg(disp_g + a0 + j1);
+            const float v10 = __ldg(disp_g + a1 + j0), v11 = __ldg(disp_g + a1 + j1);
             const float top = fmaf(lam, v01, (1.f - lam) * v00), bot = fmaf(lam, v11, (1.f - lam) * v10);
             d = fmaf(mu, bot, (1.f - mu) * top);
         } else {
-            d = __ldg(disp_b + offy);
+            d = __ldg(disp_g + bdp + offy);
         }
         const float sigma = fmaf(p.disp_range, d, p.min_disp);   // layers.py:23
         const float D = rcp_nr(sigma);                            // layers.py:24
@@ -260,7 +300,7 @@ sweep_kernel(const PhotoParams p) {
         const float r2 = rc2 + fmaf(ik7, fy, ik8);
         const float X0 = D * r0, X1 = D * r1, X2 = D * r2;       // layers.py:165
         const bool emit = col_owned && (r >= y0) && (r < y1);
-        if (ps.depth != nullptr && emit) ps.depth[(size_t)b * plane + r * W + cx] = D;
+        if (ps.depth != nullptr && emit) ps.depth[bp + r * W + cx] = D;
 
         // projection of both frames (layers.py:183-187)
         const float2 c0 = fma2(P[0], splat(X0), fma2(P[1], splat(X1), fma2(P[2], splat(X2), P[3])));
@@ -280,17 +320,25 @@ sweep_kernel(const PhotoParams p) {
         // clip backward (zero outside the open interval) times d ix / d u
         const float2 mx = f2((ixr.x > 0.f && ixr.x < wmax) ? wscale : 0.f, (ixr.y > 0.f && ixr.y < wmax) ? wscale : 0.f);
         const float2 my = f2((iyr.x > 0.f && iyr.x < hmax) ? hscale : 0.f, (iyr.y > 0.f && iyr.y < hmax) ? hscale : 0.f);
-        const int o0 = (int)fy0.x * W + (int)fx0.x, o1 = (int)fy0.y * W + (int)fx0.y;
+        const int o0 = b3p + (int)fy0.x * W + (int)fx0.x, o1 = b3p + (int)fy0.y * W + (int)fx0.y;
 
         float2 xv[3], dpx[3], dpy[3];
         float2 l1_cur = splat(0.f);
-        const float* q0 = src0_b + o0;    // one 64-bit address per frame; every other tap is a
-        const float* q1 = src1_b + o1;    // warp-uniform offset (plane, W) or the immediate +1
+        // o0 / o1: element index of the north-west tap; the others are warp-uniform offsets (plane, W)
+        // or the immediate +1
+        if (PREFETCH) {
+            // the row below this step's taps is what the next row step gathers: pull it into L1 now
+            const int dn0 = o0 + (((int)fy0.x + 2 <= H - 1) ? 2 * W : W), dn1 = o1 + (((int)fy0.y + 2 <= H - 1) ? 2 * W : W);
+            prefetch_l1(src0_g + dn0); prefetch_l1(src0_g + dn0 + plane); prefetch_l1(src0_g + dn0 + 2 * plane);
+            prefetch_l1(src1_g + dn1); prefetch_l1(src1_g + dn1 + plane); prefetch_l1(src1_g + dn1 + 2 * plane);
+        }
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const int oc = c * plane, ocw = c * plane + W;
-            const float2 nw = f2(__ldg(q0 + oc), __ldg(q1 + oc)), ne = f2(__ldg(q0 + oc + 1), __ldg(q1 + oc + 1));
-            const float2 sw = f2(__ldg(q0 + ocw), __ldg(q1 + ocw)), se = f2(__ldg(q0 + ocw + 1), __ldg(q1 + ocw + 1));
+            const float2 nw = f2(__ldg(src0_g + o0 + oc), __ldg(src1_g + o1 + oc));
+            const float2 ne = f2(__ldg(src0_g + o0 + oc + 1), __ldg(src1_g + o1 + oc + 1));
+            const float2 sw = f2(__ldg(src0_g + o0 + ocw), __ldg(src1_g + o1 + ocw));
+            const float2 se = f2(__ldg(src0_g + o0 + ocw + 1), __ldg(src1_g + o1 + ocw + 1));
             const float2 dt = sub2(ne, nw), db = sub2(se, sw);
             const float2 top = fma2(tx, dt, nw), bot = fma2(tx, db, sw);
             const float2 dvert = sub2(bot, top);
@@ -303,8 +351,8 @@ sweep_kernel(const PhotoParams p) {
             l1_cur.x += fabsf(df.x);
             l1_cur.y += fabsf(df.y);
             if (ps.warped != nullptr && emit) {
-                ps.warped[((size_t)(0 * p.B + b) * 3 + c) * plane + r * W + cx] = xv[c].x;
-                if (S > 1) ps.warped[((size_t)(1 * p.B + b) * 3 + c) * plane + r * W + cx] = xv[c].y;
+                ps.warped[b3p + c * plane + r * W + cx] = xv[c].x;
+                if (S > 1) ps.warped[(size_t)p.B * 3 * plane + b3p + c * plane + r * W + cx] = xv[c].y;
             }
         }
         if (GRAD) {
@@ -335,14 +383,12 @@ sweep_kernel(const PhotoParams p) {
                     const float2 hxn = add2(add2(xl, xv[c]), xr);
                     const float2 hxxn = fma2(xl, xl, fma2(xv[c], xv[c], mul2(xr, xr)));
                     const float2 hxyn = fma2(xl, splat(yl), fma2(xv[c], splat(yv[c]), mul2(xr, splat(yr))));
-                    const float Sy = hy2[c] + hy1[c] + hyn;
-                    const float Syy = hyy2[c] + hyy1[c] + hyyn;
-                    const float2 Sx = add2(add2(hx2[c], hx1[c]), hxn);
-                    const float2 Sxx = add2(add2(hxx2[c], hxx1[c]), hxxn);
-                    const float2 Sxy = add2(add2(hxy2[c], hxy1[c]), hxyn);
-                    hy2[c] = hy1[c]; hy1[c] = hyn; hyy2[c] = hyy1[c]; hyy1[c] = hyyn;
-                    hx2[c] = hx1[c]; hx1[c] = hxn; hxx2[c] = hxx1[c]; hxx1[c] = hxxn;
-                    hxy2[c] = hxy1[c]; hxy1[c] = hxyn;
+                    const float Sy = hyB[c] + hyA[c] + hyn;
+                    const float Syy = hyyB[c] + hyyA[c] + hyyn;
+                    const float2 Sx = add2(add2(hxB[c], hxA[c]), hxn);
+                    const float2 Sxx = add2(add2(hxxB[c], hxxA[c]), hxxn);
+                    const float2 Sxy = add2(add2(hxyB[c], hxyA[c]), hxyn);
+                    hyB[c] = hyn; hyyB[c] = hyyn; hxB[c] = hxn; hxxB[c] = hxxn; hxyB[c] = hxyn;
                     const float k9 = 1.0f / 9.0f;
                     const float my_ = Sy * k9;
                     const float myy = my_ * my_;
@@ -366,18 +412,16 @@ sweep_kernel(const PhotoParams p) {
             const int pix = py * W + cx;
             if (n_id > 0) {
                 float nz0, nz1 = 0.f;
-                if (nz_b != nullptr) {
-                    nz0 = __ldg(nz_b + pix);
-                    if (n_id > 1) nz1 = __ldg(nz_b + pix + plane);
+                if (nz_g != nullptr) {
+                    nz0 = __ldg(nz_g + bip + pix);
+                    if (n_id > 1) nz1 = __ldg(nz_g + bip + pix + plane);
                 } else {
-                    float nz[4];
-                    const size_t lin = (size_t)b * plane + pix;
-                    philox_normal4(p.seed, (uint32_t)lin, (uint32_t)(lin >> 32), (uint32_t)pass_i, nz);
-                    nz0 = nz[0]; nz1 = nz[1];
+                    philox2_normal2((uint32_t)p.seed ^ ((uint32_t)(p.seed >> 32) * 0x9E3779B9u),
+                                    (uint32_t)(b * plane + pix), (uint32_t)pass_i, nz0, nz1);
                 }
-                best = fmaf(nz0, kTieNoise, __ldg(id_b + pix));
+                best = fmaf(nz0, kTieNoise, __ldg(id_g + bip + pix));
                 if (n_id > 1) {
-                    const float cand = fmaf(nz1, kTieNoise, __ldg(id_b + pix + plane));
+                    const float cand = fmaf(nz1, kTieNoise, __ldg(id_g + bip + pix + plane));
                     if (cand < best) { best = cand; best_i = 1; }
                 }
             }
@@ -392,7 +436,7 @@ sweep_kernel(const PhotoParams p) {
             }
             if (col_owned && py >= y0 && py < y1) {
                 loss_acc += best;
-                if (ps.argmin != nullptr) ps.argmin[(size_t)b * plane + pix] = (uint8_t)best_i;
+                if (ps.argmin != nullptr) ps.argmin[bp + pix] = (uint8_t)best_i;
             }
         }
 
@@ -412,9 +456,8 @@ sweep_kernel(const PhotoParams p) {
                     const float2 cf = mul2(base, m < 3 ? pa[c] : (m < 6 ? pb[c] : pe[c]));
                     const float2 cl = shfl_up2(cf), cr = shfl_down2(cf);
                     const float2 hn = fma2(splat(wl), cl, fma2(splat(wr), cr, cf));
-                    V[m] = fma2(splat(wt), hc2[m], fma2(splat(wb), hn, hc1[m]));
-                    hc2[m] = hc1[m];
-                    hc1[m] = hn;
+                    V[m] = fma2(splat(wt), hcB[m], fma2(splat(wb), hn, hcA[m]));
+                    hcB[m] = hn;
                 }
             }
             float g_d = 0.f;
@@ -473,11 +516,16 @@ sweep_kernel(const PhotoParams p) {
                     if (i0 + 1 <= hd - 1) { acc0 = fmaf(1.f - mu, g_d, acc0); acc1 = fmaf(mu, g_d, acc1); }
                     else acc0 += g_d;
                 } else if (col_owned && ps.grad_disp != nullptr) {
-                    ps.grad_disp[(size_t)b * plane + qy * W + cx] += g_d;
+                    atomicAdd(ps.grad_disp + (bp + qy * W + cx), g_d);   // RED: fire and forget
                 }
             }
         }
         slotA = (slotA + 1 == 3) ? 0 : slotA + 1;
+    };
+#pragma unroll 1
+    for (int r = y0 - 2; r <= r_end; r += 2) {
+        step(r, hy1, hy2, hyy1, hyy2, hx1, hx2, hxx1, hxx2, hxy1, hxy2, hc1, hc2);
+        if (r + 1 <= r_end) step(r + 1, hy2, hy1, hyy2, hyy1, hx2, hx1, hxx2, hxx1, hxy2, hxy1, hc2, hc1);
     }
 
     // ------------------------------------ epilogue ------------------------------------------------

@@ -24,6 +24,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __launch_bounds__(...)
 #define __shared__ static
 #define __align__(n)
@@ -156,6 +157,8 @@ static inline float rsqrtf(float a) { return 1.0f / std::sqrt(a); }
 #define __logf(x) logf(x)
 #define __cosf(x) cosf(x)
 #define __sinf(x) sinf(x)
+static inline void emu_sincosf(float a, float* s, float* c) { *s = std::sin(a); *c = std::cos(a); }
+#define __sincosf(a, s, c) emu_sincosf(a, s, c)
 template <class T> static inline T min(T a, T b) { return a < b ? a : b; }
 template <class T> static inline T max(T a, T b) { return a > b ? a : b; }
 
