@@ -152,9 +152,7 @@ int launch_sweep(const PhotoParams& pp, cudaStream_t st) {
     const size_t smem = sweep_smem_bytes();   // < 48 KB: no opt-in needed
     if (pp.B > 65535) return PML_ERR_UNSUPPORTED;
     const dim3 grid(pp.n_chunks * pp.n_strips, pp.B, pp.n_pass);
-    static const bool prefetch = env_int("PML_PREFETCH", 1) != 0;
-    if (prefetch) PML_LAUNCH((sweep_kernel<GRAD, SSIM, true>), grid, dim3(kSweepWarps * 32), smem, st, pp);
-    else          PML_LAUNCH((sweep_kernel<GRAD, SSIM, false>), grid, dim3(kSweepWarps * 32), smem, st, pp);
+    PML_LAUNCH((sweep_kernel<GRAD, SSIM>), grid, dim3(kSweepWarps * 32), smem, st, pp);
     return PML_OK;
 }
 

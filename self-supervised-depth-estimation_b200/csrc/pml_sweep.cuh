@@ -13,14 +13,15 @@
 //    projection, bilinear taps, SSIM statistics, SSIM adjoint, pose / depth adjoint are written once
 //    and executed for both frames per instruction (S = 1 aliases frame 0 into the second half);
 //  * per-pixel geometry needed by the adjoint two rows later sits in a lane-private shared-memory
-//    ring (7 x 128-bit per row, conflict free), rolling 3x3 sums stay in registers;
-//  * all index arithmetic is 32 bit; the +1 taps of the bilinear gather are immediate offsets.
+//    ring (7 x 128-bit per row, conflict free), rolling 3x3 sums stay in registers and rotate by
+//    renaming (the row loop is unrolled by two with the roles of the two register sets swapped);
+//  * streaming inputs (target, disparity, identity losses, noise) are loaded one row step ahead of
+//    their use; all index arithmetic is 32 bit, one IMAD.WIDE per address, +1 taps are immediates.
 //
-// Layout of the work: item = ((pass * B + b) * n_chunks + chunk) * n_strips + strip, one item per
-// warp and one warp per CTA, so that everything derived from the item (image, pass, base pointers,
-// row bounds) is provably warp-uniform and lives in uniform registers / the uniform datapath
-// instead of the 255 vector registers the rolling state needs.  Each item writes one row of
-// partials (loss, 12 x S pose-gradient sums) that finalize_image_kernel reduces in fixed order.
+// Layout of the work: grid = (n_chunks * n_strips, B, n_pass), one warp per CTA, so that image and
+// pass are warp-uniform by construction.  item = ((pass * B + b) * n_chunks + chunk) * n_strips +
+// strip writes one row of partials (loss, 12 x S pose-gradient sums) that finalize_image_kernel
+// reduces in fixed order.
 #pragma once
 #include "pml_common.cuh"
 #include "pml_photometric.cuh"
@@ -45,13 +46,18 @@ __device__ __forceinline__ float2 shfl_up2(float2 v) {
 __device__ __forceinline__ float2 shfl_down2(float2 v) {
     return make_float2(__shfl_down_sync(0xffffffffu, v.x, 1), __shfl_down_sync(0xffffffffu, v.y, 1));
 }
-// L1 prefetch of one line (CCTL.E.PF1): no destination register, never waited on
-__device__ __forceinline__ void prefetch_l1(const void* ptr) {
-#ifndef PML_HOST_EMU
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
+// base + 32-bit element index as ONE instruction (IMAD.WIDE); tensors have < 2^31 elements
+__device__ __forceinline__ const float* at(const float* base, int idx) {
+#ifdef PML_HOST_EMU
+    return base + idx;
 #else
-    (void)ptr;
+    const float* r;
+    asm("mad.wide.s32 %0, %1, 4, %2;" : "=l"(r) : "r"(idx), "l"(base));
+    return r;
 #endif
+}
+__device__ __forceinline__ float* at(float* base, int idx) {
+    return const_cast<float*>(at(static_cast<const float*>(base), idx));
 }
 // MUFU.RCP (1 ulp); callers add the Newton step where the quotient decides something
 __device__ __forceinline__ float rcp_approx(float x) {
@@ -131,7 +137,7 @@ __device__ __noinline__ void sweep_flush_row(float* sG, float* gd_row, float h, 
     __syncwarp();
 }
 
-template <bool GRAD, bool SSIM, bool PREFETCH>
+template <bool GRAD, bool SSIM>
 __global__ void __launch_bounds__(kSweepWarps * 32)
 sweep_kernel(const PhotoParams p) {
     PML_DYN_SMEM(float, smem);
@@ -160,44 +166,47 @@ sweep_kernel(const PhotoParams p) {
 
     // ---- per-warp shared memory ----------------------------------------------------------------
     float* wsm = smem;
-    float2* sP = reinterpret_cast<float2*>(wsm);          // [12] (frame0, frame1) of P = (K T)[:3]
-    float* sIK = wsm + 24;                                 // [9] inv_K 3x3 (+ pad to 48)
+    const float4* sP4 = reinterpret_cast<const float4*>(wsm);        // [6]: 12 x (frame0, frame1) of P = (K T)[:3]
+    const float4* sIK4 = reinterpret_cast<const float4*>(wsm + 24);  // inv_K: [0][1] [0][2] [1][1] [1][2] | [2][1] [2][2]
     float* sG = wsm + 48;                                  // [32] staging row of the transposed upsample
     float4* sRing = reinterpret_cast<float4*>(wsm + 80);   // [3][kSweepRingQ][32]
 
-    if (lane < 24) {
-        const int e = lane >> 1, f = (lane & 1) ? f1 : 0, i = e >> 2, j = e & 3;
-        const float* Kb = p.K + b * 16;
-        const float* Tb = p.T[f] + b * 16;
-        float a = 0.f;
+    float rc0, rc1, rc2;    // column part of the back-projection ray r = inv_K[:3,:3] @ (x, y, 1)
+    {
+        if (lane < 24) {
+            const int e = lane >> 1, f = (lane & 1) ? f1 : 0, i = e >> 2, j = e & 3;
+            const float* Kb = p.K + b * 16;
+            const float* Tb = p.T[f] + b * 16;
+            float a = 0.f;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) a = fmaf(Kb[i * 4 + k], Tb[k * 4 + j], a);   // layers.py:183
-        wsm[lane] = a;
+            for (int k = 0; k < 4; ++k) a = fmaf(Kb[i * 4 + k], Tb[k * 4 + j], a);   // layers.py:183
+            wsm[lane] = a;
+        }
+        const float* ikb = p.invK + b * 16;                                          // layers.py:164
+        if (lane == 0) {
+            wsm[24] = ikb[1]; wsm[25] = ikb[2]; wsm[26] = ikb[5]; wsm[27] = ikb[6];
+            wsm[28] = ikb[9]; wsm[29] = ikb[10]; wsm[30] = 0.f; wsm[31] = 0.f;
+        }
+        const float fxc = (float)rx;
+        rc0 = ikb[0] * fxc; rc1 = ikb[4] * fxc; rc2 = ikb[8] * fxc;
+        __syncwarp();
     }
-    if (lane < 9) sIK[lane] = p.invK[b * 16 + (lane / 3) * 4 + (lane % 3)];      // layers.py:164
-    __syncwarp();
-
-    float2 P[12];
-#pragma unroll
-    for (int e = 0; e < 12; ++e) P[e] = sP[e];
-    const float ik1 = sIK[1], ik2 = sIK[2], ik4 = sIK[4], ik5 = sIK[5], ik7 = sIK[7], ik8 = sIK[8];
-    const float fxc = (float)rx;
-    const float rc0 = sIK[0] * fxc, rc1 = sIK[3] * fxc, rc2 = sIK[6] * fxc;
 
     // horizontal part of the disparity upsample (trainer.py:474): fixed per lane
     const int kk = ps.k, wd = ps.wd, hd = ps.hd;
+    const float rscale = ps.rscale;
     int j0 = rx, j1 = rx;
     float lam = 0.f;
     if (kk > 1) {
-        const float sx = fmaxf(fmaf(ps.rscale, (float)rx + 0.5f, -0.5f), 0.f);
+        const float sx = fmaxf(fmaf(rscale, (float)rx + 0.5f, -0.5f), 0.f);
         j0 = (int)sx;
         j1 = min(j0 + 1, wd - 1);
         lam = sx - (float)j0;
     }
 
     const int plane = H * W;
-    // All global addressing is `parameter pointer [32-bit element index]` (one IMAD.WIDE per address):
-    // every tensor of a call has < 2^31 elements (checked on the host).
+    // All global addressing is `parameter pointer [32-bit element index]`: every tensor of a call has
+    // fewer than 2^31 elements (checked on the host).
     const float* __restrict__ tgt_g = p.target;
     const float* __restrict__ src0_g = p.src[0];
     const float* __restrict__ src1_g = p.src[f1];
@@ -211,6 +220,7 @@ sweep_kernel(const PhotoParams p) {
     const float wscale = (float)W / (float)(W - 1), hscale = (float)H / (float)(H - 1);
     const float wmax = (float)(W - 1), hmax = (float)(H - 1);
     const float wmax1 = (float)(W - 2), hmax1 = (float)(H - 2);
+    const bool emit_any = (ps.depth != nullptr) || (ps.warped != nullptr);
 
     // ---- rolling state ---------------------------------------------------------------------------
     float hy1[3], hy2[3], hyy1[3], hyy2[3];
@@ -233,8 +243,8 @@ sweep_kernel(const PhotoParams p) {
     float acc0 = 0.f, acc1 = 0.f;
     int cur = 0, jbase = 0;
     if (GRAD && kk > 1) {
-        cur = (int)fmaxf(fmaf(ps.rscale, (float)y0 + 0.5f, -0.5f), 0.f);
-        jbase = (int)fmaxf(fmaf(ps.rscale, (float)x0 + 0.5f, -0.5f), 0.f);
+        cur = (int)fmaxf(fmaf(rscale, (float)y0 + 0.5f, -0.5f), 0.f);
+        jbase = (int)fmaxf(fmaf(rscale, (float)x0 + 0.5f, -0.5f), 0.f);
     }
     const int low_cols = kSweepTW / kk + 3;
 
@@ -243,9 +253,27 @@ sweep_kernel(const PhotoParams p) {
     const float kl1 = SSIM ? (0.15f / 3.0f) : (1.0f / 3.0f);
 
     auto flush_row = [&](int irow, float h) {
-        sweep_flush_row(sG, ps.grad_disp + (bdp + irow * wd), h, lane, jbase, low_cols, wd, kk, x0, x1,
-                        ps.rscale);
+        sweep_flush_row(sG, ps.grad_disp + (bdp + irow * wd), h, lane, jbase, low_cols, wd, kk, x0, x1, rscale);
     };
+
+    // Streaming inputs of one row, issued one row step before they are consumed: target colours and
+    // the (up to four) disparity values around (rx, ry).
+    float yn[3], dn[4];
+    auto load_row = [&](int r) {
+        const int ry = reflect1(clampi(r, -1, H), H);
+        const float* tq = at(tgt_g, b3p + ry * W + rx);
+        yn[0] = __ldg(tq); yn[1] = __ldg(at(tq, plane)); yn[2] = __ldg(at(tq, 2 * plane));
+        if (kk > 1) {
+            const float sy = fmaxf(fmaf(rscale, (float)ry + 0.5f, -0.5f), 0.f);
+            const int i0 = (int)sy, i1 = min(i0 + 1, hd - 1);
+            const float* d0 = at(disp_g, bdp + i0 * wd);
+            const float* d1 = at(disp_g, bdp + i1 * wd);
+            dn[0] = __ldg(at(d0, j0)); dn[1] = __ldg(at(d0, j1)); dn[2] = __ldg(at(d1, j0)); dn[3] = __ldg(at(d1, j1));
+        } else {
+            dn[0] = __ldg(at(disp_g, bdp + ry * W + rx));
+        }
+    };
+    load_row(y0 - 2);
 
     int slotA = 0;   // ring slot of row r; (slotA+2)%3 holds row r-1, (slotA+1)%3 row r-2
     const int r_end = GRAD ? (y1 + 1) : y1;
@@ -257,55 +285,49 @@ sweep_kernel(const PhotoParams p) {
                     float2 (&hxyA)[3], float2 (&hxyB)[3], float2 (&hcA)[GRAD ? 9 : 1], float2 (&hcB)[GRAD ? 9 : 1]) {
         // =================================== (A) warp row r ======================================
         const int ry = reflect1(clampi(r, -1, H), H);
-        const int offy = ry * W + rx;
-        float yv[3];
-        {
-            const int ty_ = b3p + offy;
-            yv[0] = __ldg(tgt_g + ty_); yv[1] = __ldg(tgt_g + ty_ + plane); yv[2] = __ldg(tgt_g + ty_ + 2 * plane);
-            if (PREFETCH) {
-                // streaming inputs of the next row step: target row r+1, identity / noise of window row r
-                const int rn = reflect1(clampi(r + 1, -1, H), H) - ry;   // -1, 0 or +1 rows
-                const int tn = ty_ + rn * W;
-                prefetch_l1(tgt_g + tn); prefetch_l1(tgt_g + tn + plane); prefetch_l1(tgt_g + tn + 2 * plane);
-                if (kk == 1) prefetch_l1(disp_g + bdp + offy + rn * W);
-                if (n_id > 0) {
-                    const int pr = bip + clampi(r, 0, H - 1) * W + rx;
-                    prefetch_l1(id_g + pr);
-                    if (nz_g != nullptr) prefetch_l1(nz_g + pr);
-                    if (n_id > 1) {
-                        prefetch_l1(id_g + pr + plane);
-                        if (nz_g != nullptr) prefetch_l1(nz_g + pr + plane);
-                    }
-                }
-            }
-        }
+        const float yv[3] = {yn[0], yn[1], yn[2]};
         float d;
         if (kk > 1) {   // bilinear upsample of disp_s, align_corners=False (trainer.py:474)
-            const float sy = fmaxf(fmaf(ps.rscale, (float)ry + 0.5f, -0.5f), 0.f);
-            const int i0 = (int)sy, i1 = min(i0 + 1, hd - 1);
-            const float mu = sy - (float)i0;
-            const int a0 = bdp + i0 * wd, a1 = bdp + i1 * wd;
-            const float v00 = __ldg(disp_g + a0 + j0), v01 = __ldg(disp_g + a0 + j1);
-            const float v10 = __ldg(disp_g + a1 + j0), v11 = __ldg(disp_g + a1 + j1);
-            const float top = fmaf(lam, v01, (1.f - lam) * v00), bot = fmaf(lam, v11, (1.f - lam) * v10);
+            const float sy = fmaxf(fmaf(rscale, (float)ry + 0.5f, -0.5f), 0.f);
+            const float mu = sy - floorf(sy);
+            const float top = fmaf(lam, dn[1], (1.f - lam) * dn[0]), bot = fmaf(lam, dn[3], (1.f - lam) * dn[2]);
             d = fmaf(mu, bot, (1.f - mu) * top);
         } else {
-            d = __ldg(disp_g + bdp + offy);
+            d = dn[0];
         }
+        load_row(r + 1);   // consumed by the next step
+        // identity losses / noise of the window row r-1 (used at the end of (B)); clamped so that the
+        // early, unconditional loads stay inside the tensors
+        const int py = r - 1;
+        float idv0 = 0.f, idv1 = 0.f, nzv0 = 0.f, nzv1 = 0.f;
+        if (n_id > 0) {
+            const float* ic = at(id_g, bip + clampi(py, 0, H - 1) * W + rx);
+            idv0 = __ldg(ic);
+            if (n_id > 1) idv1 = __ldg(at(ic, plane));
+            if (nz_g != nullptr) {
+                const float* nc = at(nz_g, bip + clampi(py, 0, H - 1) * W + rx);
+                nzv0 = __ldg(nc);
+                if (n_id > 1) nzv1 = __ldg(at(nc, plane));
+            }
+        }
+
         const float sigma = fmaf(p.disp_range, d, p.min_disp);   // layers.py:23
         const float D = rcp_nr(sigma);                            // layers.py:24
         const float fy = (float)ry;
-        const float r0 = rc0 + fmaf(ik1, fy, ik2);
-        const float r1 = rc1 + fmaf(ik4, fy, ik5);
-        const float r2 = rc2 + fmaf(ik7, fy, ik8);
+        const float4 ika = sIK4[0], ikb4 = sIK4[1];
+        const float r0 = rc0 + fmaf(ika.x, fy, ika.y);
+        const float r1 = rc1 + fmaf(ika.z, fy, ika.w);
+        const float r2 = rc2 + fmaf(ikb4.x, fy, ikb4.y);
         const float X0 = D * r0, X1 = D * r1, X2 = D * r2;       // layers.py:165
-        const bool emit = col_owned && (r >= y0) && (r < y1);
-        if (ps.depth != nullptr && emit) ps.depth[bp + r * W + cx] = D;
 
-        // projection of both frames (layers.py:183-187)
-        const float2 c0 = fma2(P[0], splat(X0), fma2(P[1], splat(X1), fma2(P[2], splat(X2), P[3])));
-        const float2 c1 = fma2(P[4], splat(X0), fma2(P[5], splat(X1), fma2(P[6], splat(X2), P[7])));
-        const float2 c2 = fma2(P[8], splat(X0), fma2(P[9], splat(X1), fma2(P[10], splat(X2), P[11])));
+        // projection of both frames (layers.py:183-187); P comes from shared memory (broadcast)
+        float2 c0, c1, c2;
+        {
+            const float4 pa0 = sP4[0], pa1 = sP4[1], pb0 = sP4[2], pb1 = sP4[3], pc0 = sP4[4], pc1 = sP4[5];
+            c0 = fma2(f2(pa0.x, pa0.y), splat(X0), fma2(f2(pa0.z, pa0.w), splat(X1), fma2(f2(pa1.x, pa1.y), splat(X2), f2(pa1.z, pa1.w))));
+            c1 = fma2(f2(pb0.x, pb0.y), splat(X0), fma2(f2(pb0.z, pb0.w), splat(X1), fma2(f2(pb1.x, pb1.y), splat(X2), f2(pb1.z, pb1.w))));
+            c2 = fma2(f2(pc0.x, pc0.y), splat(X0), fma2(f2(pc0.z, pc0.w), splat(X1), fma2(f2(pc1.x, pc1.y), splat(X2), f2(pc1.z, pc1.w))));
+        }
         const float2 invz = rcp_nr2(add2(c2, splat(p.eps)));
         const float2 u = mul2(c0, invz), v = mul2(c1, invz);
         // layers.py:190-192 + grid_sample unnormalise (align_corners=False): ix = u*W/(W-1) - 0.5
@@ -320,25 +342,21 @@ sweep_kernel(const PhotoParams p) {
         // clip backward (zero outside the open interval) times d ix / d u
         const float2 mx = f2((ixr.x > 0.f && ixr.x < wmax) ? wscale : 0.f, (ixr.y > 0.f && ixr.y < wmax) ? wscale : 0.f);
         const float2 my = f2((iyr.x > 0.f && iyr.x < hmax) ? hscale : 0.f, (iyr.y > 0.f && iyr.y < hmax) ? hscale : 0.f);
-        const int o0 = b3p + (int)fy0.x * W + (int)fx0.x, o1 = b3p + (int)fy0.y * W + (int)fx0.y;
+        // address of the north-west tap; the other taps are warp-uniform offsets (plane, W) from it,
+        // or the immediate +1
+        const float* q0 = at(src0_g, b3p + (int)fy0.x * W + (int)fx0.x);
+        const float* q1 = at(src1_g, b3p + (int)fy0.y * W + (int)fx0.y);
 
         float2 xv[3], dpx[3], dpy[3];
         float2 l1_cur = splat(0.f);
-        // o0 / o1: element index of the north-west tap; the others are warp-uniform offsets (plane, W)
-        // or the immediate +1
-        if (PREFETCH) {
-            // the row below this step's taps is what the next row step gathers: pull it into L1 now
-            const int dn0 = o0 + (((int)fy0.x + 2 <= H - 1) ? 2 * W : W), dn1 = o1 + (((int)fy0.y + 2 <= H - 1) ? 2 * W : W);
-            prefetch_l1(src0_g + dn0); prefetch_l1(src0_g + dn0 + plane); prefetch_l1(src0_g + dn0 + 2 * plane);
-            prefetch_l1(src1_g + dn1); prefetch_l1(src1_g + dn1 + plane); prefetch_l1(src1_g + dn1 + 2 * plane);
-        }
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const int oc = c * plane, ocw = c * plane + W;
-            const float2 nw = f2(__ldg(src0_g + o0 + oc), __ldg(src1_g + o1 + oc));
-            const float2 ne = f2(__ldg(src0_g + o0 + oc + 1), __ldg(src1_g + o1 + oc + 1));
-            const float2 sw = f2(__ldg(src0_g + o0 + ocw), __ldg(src1_g + o1 + ocw));
-            const float2 se = f2(__ldg(src0_g + o0 + ocw + 1), __ldg(src1_g + o1 + ocw + 1));
+            const float* a0 = (c == 0) ? q0 : at(q0, c * plane);
+            const float* a1 = (c == 0) ? q1 : at(q1, c * plane);
+            const float* w0 = at(q0, c * plane + W);
+            const float* w1 = at(q1, c * plane + W);
+            const float2 nw = f2(__ldg(a0), __ldg(a1)), ne = f2(__ldg(a0 + 1), __ldg(a1 + 1));
+            const float2 sw = f2(__ldg(w0), __ldg(w1)), se = f2(__ldg(w0 + 1), __ldg(w1 + 1));
             const float2 dt = sub2(ne, nw), db = sub2(se, sw);
             const float2 top = fma2(tx, dt, nw), bot = fma2(tx, db, sw);
             const float2 dvert = sub2(bot, top);
@@ -350,9 +368,16 @@ sweep_kernel(const PhotoParams p) {
             const float2 df = sub2(xv[c], splat(yv[c]));
             l1_cur.x += fabsf(df.x);
             l1_cur.y += fabsf(df.y);
-            if (ps.warped != nullptr && emit) {
-                ps.warped[b3p + c * plane + r * W + cx] = xv[c].x;
-                if (S > 1) ps.warped[(size_t)p.B * 3 * plane + b3p + c * plane + r * W + cx] = xv[c].y;
+        }
+        if (emit_any && col_owned && (r >= y0) && (r < y1)) {   // trainer.py:480, :508 (on request)
+            const int o = r * W + cx;
+            if (ps.depth != nullptr) ps.depth[bp + o] = D;
+            if (ps.warped != nullptr) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    ps.warped[b3p + c * plane + o] = xv[c].x;
+                    if (S > 1) ps.warped[(size_t)p.B * 3 * plane + b3p + c * plane + o] = xv[c].y;
+                }
             }
         }
         if (GRAD) {
@@ -367,7 +392,6 @@ sweep_kernel(const PhotoParams p) {
         }
 
         // ========================= (B) close the windows centred on row r-1 ======================
-        const int py = r - 1;
         const bool p_valid = (r >= y0) && (py >= 0) && (py < H) && col_in_image && lane_inner;
         float2 rp = splat(0.f);
         float2 pa[3], pb[3], pe[3];
@@ -411,17 +435,12 @@ sweep_kernel(const PhotoParams p) {
             int best_i = 0;
             const int pix = py * W + cx;
             if (n_id > 0) {
-                float nz0, nz1 = 0.f;
-                if (nz_g != nullptr) {
-                    nz0 = __ldg(nz_g + bip + pix);
-                    if (n_id > 1) nz1 = __ldg(nz_g + bip + pix + plane);
-                } else {
+                if (nz_g == nullptr)
                     philox2_normal2((uint32_t)p.seed ^ ((uint32_t)(p.seed >> 32) * 0x9E3779B9u),
-                                    (uint32_t)(b * plane + pix), (uint32_t)pass_i, nz0, nz1);
-                }
-                best = fmaf(nz0, kTieNoise, __ldg(id_g + bip + pix));
+                                    (uint32_t)(bp + pix), (uint32_t)pass_i, nzv0, nzv1);
+                best = fmaf(nzv0, kTieNoise, idv0);
                 if (n_id > 1) {
-                    const float cand = fmaf(nz1, kTieNoise, __ldg(id_g + bip + pix + plane));
+                    const float cand = fmaf(nzv1, kTieNoise, idv1);
                     if (cand < best) { best = cand; best_i = 1; }
                 }
             }
@@ -444,7 +463,7 @@ sweep_kernel(const PhotoParams p) {
         if (GRAD) {
             const float2 wsc = mul2(wgt, splat(p.inv_n));      // winner weight of window row r-1
             const int qy = r - 2;
-            const bool do_q = (r >= y0 + 2);                   // => y0 <= qy < y1
+            const bool do_q = (r >= y0 + 2) && (qy < y1);      // y0 <= qy < y1
             const float wt = (qy == 1) ? 2.f : 1.f, wb = (qy == H - 2) ? 2.f : 1.f;   // reflection fold (rows)
             float2 V[9];
             if (SSIM) {
@@ -463,14 +482,14 @@ sweep_kernel(const PhotoParams p) {
             float g_d = 0.f;
             if (do_q && col_owned) {
                 const float4* rc = sRing + (((slotA + 1) % 3) * kSweepRingQ) * 32 + lane;
-                const float4 q0 = rc[0 * 32], q1 = rc[1 * 32], q2 = rc[2 * 32], q3 = rc[3 * 32];
-                const float4 q4 = rc[4 * 32], q5 = rc[5 * 32], q6 = rc[6 * 32];
-                const float yq[3] = {q0.x, q0.y, q0.z};
-                const float Dq = q0.w;
-                const float2 xq[3] = {f2(q1.x, q1.y), f2(q1.z, q1.w), f2(q2.x, q2.y)};
-                const float2 dxq[3] = {f2(q2.z, q2.w), f2(q3.x, q3.y), f2(q3.z, q3.w)};
-                const float2 dyq[3] = {f2(q4.x, q4.y), f2(q4.z, q4.w), f2(q5.x, q5.y)};
-                const float2 invzq = f2(q5.z, q5.w), uq = f2(q6.x, q6.y), vq = f2(q6.z, q6.w);
+                const float4 q0r = rc[0 * 32], q1r = rc[1 * 32], q2r = rc[2 * 32], q3r = rc[3 * 32];
+                const float4 q4r = rc[4 * 32], q5r = rc[5 * 32], q6r = rc[6 * 32];
+                const float yq[3] = {q0r.x, q0r.y, q0r.z};
+                const float Dq = q0r.w;
+                const float2 xq[3] = {f2(q1r.x, q1r.y), f2(q1r.z, q1r.w), f2(q2r.x, q2r.y)};
+                const float2 dxq[3] = {f2(q2r.z, q2r.w), f2(q3r.x, q3r.y), f2(q3r.z, q3r.w)};
+                const float2 dyq[3] = {f2(q4r.x, q4r.y), f2(q4r.z, q4r.w), f2(q5r.x, q5r.y)};
+                const float2 invzq = f2(q5r.z, q5r.w), uq = f2(q6r.x, q6r.y), vq = f2(q6r.z, q6r.w);
                 const float2 kw = mul2(wq_prev, splat(kl1));   // wq_prev: winner weight of row r-2
                 float2 du = splat(0.f), dv = splat(0.f);
 #pragma unroll
@@ -489,7 +508,9 @@ sweep_kernel(const PhotoParams p) {
                 const float2 t = fma2(uq, du, mul2(vq, dv));
                 const float2 dc2 = mul2(f2(-t.x, -t.y), invzq);
                 const float fq = (float)qy;
-                const float rq0 = rc0 + fmaf(ik1, fq, ik2), rq1 = rc1 + fmaf(ik4, fq, ik5), rq2 = rc2 + fmaf(ik7, fq, ik8);
+                const float4 ikq = sIK4[0], ikq2 = sIK4[1];
+                const float rq0 = rc0 + fmaf(ikq.x, fq, ikq.y), rq1 = rc1 + fmaf(ikq.z, fq, ikq.w);
+                const float rq2 = rc2 + fmaf(ikq2.x, fq, ikq2.y);
                 const float Xq0 = Dq * rq0, Xq1 = Dq * rq1, Xq2 = Dq * rq2;
                 gP[0] = fma2(dc0, splat(Xq0), gP[0]); gP[1] = fma2(dc0, splat(Xq1), gP[1]);
                 gP[2] = fma2(dc0, splat(Xq2), gP[2]); gP[3] = add2(gP[3], dc0);
@@ -497,16 +518,18 @@ sweep_kernel(const PhotoParams p) {
                 gP[6] = fma2(dc1, splat(Xq2), gP[6]); gP[7] = add2(gP[7], dc1);
                 gP[8] = fma2(dc2, splat(Xq0), gP[8]); gP[9] = fma2(dc2, splat(Xq1), gP[9]);
                 gP[10] = fma2(dc2, splat(Xq2), gP[10]); gP[11] = add2(gP[11], dc2);
-                const float2 gX0 = fma2(P[0], dc0, fma2(P[4], dc1, mul2(P[8], dc2)));
-                const float2 gX1 = fma2(P[1], dc0, fma2(P[5], dc1, mul2(P[9], dc2)));
-                const float2 gX2 = fma2(P[2], dc0, fma2(P[6], dc1, mul2(P[10], dc2)));
+                // gX = P[:, :3]^T dc
+                const float4 pa0 = sP4[0], pa1 = sP4[1], pb0 = sP4[2], pb1 = sP4[3], pc0 = sP4[4], pc1 = sP4[5];
+                const float2 gX0 = fma2(f2(pa0.x, pa0.y), dc0, fma2(f2(pb0.x, pb0.y), dc1, mul2(f2(pc0.x, pc0.y), dc2)));
+                const float2 gX1 = fma2(f2(pa0.z, pa0.w), dc0, fma2(f2(pb0.z, pb0.w), dc1, mul2(f2(pc0.z, pc0.w), dc2)));
+                const float2 gX2 = fma2(f2(pa1.x, pa1.y), dc0, fma2(f2(pb1.x, pb1.y), dc1, mul2(f2(pc1.x, pc1.y), dc2)));
                 const float2 gD = fma2(splat(rq0), gX0, fma2(splat(rq1), gX1, mul2(splat(rq2), gX2)));
                 g_d = -p.disp_range * Dq * Dq * (gD.x + gD.y);   // d(1/sigma)/d disp, both frames
             }
             wq_prev = wsc;
             if (do_q) {
                 if (kk > 1) {
-                    const float sy = fmaxf(fmaf(ps.rscale, (float)qy + 0.5f, -0.5f), 0.f);
+                    const float sy = fmaxf(fmaf(rscale, (float)qy + 0.5f, -0.5f), 0.f);
                     const int i0 = (int)sy;
                     const float mu = sy - (float)i0;
                     if (i0 > cur) {            // low-res row `cur` is complete (warp-uniform)
@@ -516,16 +539,18 @@ sweep_kernel(const PhotoParams p) {
                     if (i0 + 1 <= hd - 1) { acc0 = fmaf(1.f - mu, g_d, acc0); acc1 = fmaf(mu, g_d, acc1); }
                     else acc0 += g_d;
                 } else if (col_owned && ps.grad_disp != nullptr) {
-                    atomicAdd(ps.grad_disp + (bp + qy * W + cx), g_d);   // RED: fire and forget
+                    atomicAdd(at(ps.grad_disp, bp + qy * W + cx), g_d);   // RED: fire and forget
                 }
             }
         }
         slotA = (slotA + 1 == 3) ? 0 : slotA + 1;
     };
+    // Always an even number of steps: a possible extra step past r_end only evaluates rows nobody
+    // owns (no emission, do_q false), and keeps the unrolled loop free of a conditional join.
 #pragma unroll 1
     for (int r = y0 - 2; r <= r_end; r += 2) {
         step(r, hy1, hy2, hyy1, hyy2, hx1, hx2, hxx1, hxx2, hxy1, hxy2, hc1, hc2);
-        if (r + 1 <= r_end) step(r + 1, hy2, hy1, hyy2, hyy1, hx2, hx1, hxx2, hxx1, hxy2, hxy1, hc2, hc1);
+        step(r + 1, hy2, hy1, hyy2, hyy1, hx2, hx1, hxx2, hxx1, hxy2, hxy1, hc2, hc1);
     }
 
     // ------------------------------------ epilogue ------------------------------------------------
