@@ -31,7 +31,8 @@ namespace pml {
 constexpr int kSweepWarps = 1;    // warps (= items) per CTA
 constexpr int kSweepTW = 28;      // owned columns per strip
 constexpr int kSweepRingQ = 7;    // float4 per lane per ring slot
-constexpr int kSweepWarpFloats = 48 + 32 + 3 * kSweepRingQ * 4 * 32;   // P/IK, staging row, ring
+constexpr int kSweepRingSlots = 4;   // rows r .. r-3 (the adjoint of row r-3 runs while row r's taps are in flight)
+constexpr int kSweepWarpFloats = 48 + 32 + kSweepRingSlots * kSweepRingQ * 4 * 32;   // P/IK, staging row, ring
 
 // ---- packed fp32x2 helpers (FFMA2 / FMUL2 / FADD2 on sm_100a) -----------------------------------
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
@@ -169,7 +170,7 @@ sweep_kernel(const PhotoParams p) {
     const float4* sP4 = reinterpret_cast<const float4*>(wsm);        // [6]: 12 x (frame0, frame1) of P = (K T)[:3]
     const float4* sIK4 = reinterpret_cast<const float4*>(wsm + 24);  // inv_K: [0][1] [0][2] [1][1] [1][2] | [2][1] [2][2]
     float* sG = wsm + 48;                                  // [32] staging row of the transposed upsample
-    float4* sRing = reinterpret_cast<float4*>(wsm + 80);   // [3][kSweepRingQ][32]
+    float4* sRing = reinterpret_cast<float4*>(wsm + 80);   // [kSweepRingSlots][kSweepRingQ][32]
 
     float rc0, rc1, rc2;    // column part of the back-projection ray r = inv_K[:3,:3] @ (x, y, 1)
     {
@@ -238,7 +239,10 @@ sweep_kernel(const PhotoParams p) {
     for (int e = 0; e < (GRAD ? 12 : 1); ++e) gP[e] = splat(0.f);
     float loss_acc = 0.f;
     float2 l1_prev = splat(0.f);     // sum_c |target - pred| of the previous row
-    float2 wq_prev = splat(0.f);     // winner weight / N of the previous window row
+    float2 wq1 = splat(0.f), wq2 = splat(0.f);   // winner weight / N of window rows r-2 and r-3
+    float2 cfc[GRAD ? 9 : 1];        // adjoint coefficients of window row r-2 (consumed one step later)
+#pragma unroll
+    for (int m = 0; m < (GRAD ? 9 : 1); ++m) cfc[m] = splat(0.f);
     // transposed vertical upsample: low-res rows `cur` and `cur + 1` accumulate in registers
     float acc0 = 0.f, acc1 = 0.f;
     int cur = 0, jbase = 0;
@@ -275,8 +279,8 @@ sweep_kernel(const PhotoParams p) {
     };
     load_row(y0 - 2);
 
-    int slotA = 0;   // ring slot of row r; (slotA+2)%3 holds row r-1, (slotA+1)%3 row r-2
-    const int r_end = GRAD ? (y1 + 1) : y1;
+    int slotA = 0;   // ring slot of row r; slot (slotA + 1) & 3 holds row r-3
+    const int r_end = GRAD ? (y1 + 2) : y1;
     // One row step.  The rolling 3x3 sums are passed as (previous row, row before): the step reads
     // both and overwrites the older one, so calling it with the two sets swapped on alternate rows
     // (loop unrolled by two below) rotates the window without a single register move.
@@ -347,18 +351,105 @@ sweep_kernel(const PhotoParams p) {
         const float* q0 = at(src0_g, b3p + (int)fy0.x * W + (int)fx0.x);
         const float* q1 = at(src1_g, b3p + (int)fy0.y * W + (int)fx0.y);
 
-        float2 xv[3], dpx[3], dpy[3];
-        float2 l1_cur = splat(0.f);
+        // ---- issue the 24 taps of row r; they are consumed after the adjoint below ----
+        float2 nw[3], ne[3], sw[3], se[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const float* a0 = (c == 0) ? q0 : at(q0, c * plane);
             const float* a1 = (c == 0) ? q1 : at(q1, c * plane);
             const float* w0 = at(q0, c * plane + W);
             const float* w1 = at(q1, c * plane + W);
-            const float2 nw = f2(__ldg(a0), __ldg(a1)), ne = f2(__ldg(a0 + 1), __ldg(a1 + 1));
-            const float2 sw = f2(__ldg(w0), __ldg(w1)), se = f2(__ldg(w0 + 1), __ldg(w1 + 1));
-            const float2 dt = sub2(ne, nw), db = sub2(se, sw);
-            const float2 top = fma2(tx, dt, nw), bot = fma2(tx, db, sw);
+            nw[c] = f2(__ldg(a0), __ldg(a1)); ne[c] = f2(__ldg(a0 + 1), __ldg(a1 + 1));
+            sw[c] = f2(__ldg(w0), __ldg(w1)); se[c] = f2(__ldg(w0 + 1), __ldg(w1 + 1));
+        }
+
+        // ============ (C) adjoint for the pixels of row r-3, while the taps are in flight ==========
+        // cfc: coefficients of window row r-2 (previous step); wq2: winner weight of row r-3
+        if (GRAD) {
+            const int qy = r - 3;
+            const bool do_q = (qy >= y0) && (qy < y1);
+            const float wt = (qy == 1) ? 2.f : 1.f, wb = (qy == H - 2) ? 2.f : 1.f;   // reflection fold (rows)
+            float2 V[9];
+            if (SSIM) {
+#pragma unroll
+                for (int m = 0; m < 9; ++m) {
+                    const float2 cf = cfc[m];
+                    const float2 cl = shfl_up2(cf), cr = shfl_down2(cf);
+                    const float2 hn = fma2(splat(wl), cl, fma2(splat(wr), cr, cf));
+                    V[m] = fma2(splat(wt), hcB[m], fma2(splat(wb), hn, hcA[m]));
+                    hcB[m] = hn;
+                }
+            }
+            float g_d = 0.f;
+            if (do_q && col_owned) {
+                const float4* rc = sRing + (((slotA + 1) & 3) * kSweepRingQ) * 32 + lane;
+                const float4 q0r = rc[0 * 32], q1r = rc[1 * 32], q2r = rc[2 * 32], q3r = rc[3 * 32];
+                const float4 q4r = rc[4 * 32], q5r = rc[5 * 32], q6r = rc[6 * 32];
+                const float yq[3] = {q0r.x, q0r.y, q0r.z};
+                const float Dq = q0r.w;
+                const float2 xq[3] = {f2(q1r.x, q1r.y), f2(q1r.z, q1r.w), f2(q2r.x, q2r.y)};
+                const float2 dxq[3] = {f2(q2r.z, q2r.w), f2(q3r.x, q3r.y), f2(q3r.z, q3r.w)};
+                const float2 dyq[3] = {f2(q4r.x, q4r.y), f2(q4r.z, q4r.w), f2(q5r.x, q5r.y)};
+                const float2 invzq = f2(q5r.z, q5r.w), uq = f2(q6r.x, q6r.y), vq = f2(q6r.z, q6r.w);
+                const float2 kw = mul2(wq2, splat(kl1));
+                float2 du = splat(0.f), dv = splat(0.f);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float2 df = sub2(xq[c], splat(yq[c]));
+                    // d|x - y| / dx = sign(x - y).  sign(0) is taken as +1 instead of the reference's 0:
+                    // exact equality of a warped value and the target only happens on locally constant
+                    // images, where the bilinear slopes that multiply this term are exactly 0
+                    const float2 sg = f2(copysignf(kw.x, df.x), copysignf(kw.y, df.y));
+                    float2 g = sg;
+                    if (SSIM) g = add2(g, fma2(xq[c], V[3 + c], fma2(splat(yq[c]), V[6 + c], V[c])));
+                    du = fma2(g, dxq[c], du);
+                    dv = fma2(g, dyq[c], dv);
+                }
+                const float2 dc0 = mul2(du, invzq), dc1 = mul2(dv, invzq);
+                const float2 t = fma2(uq, du, mul2(vq, dv));
+                const float2 dc2 = mul2(f2(-t.x, -t.y), invzq);
+                const float fq = (float)qy;
+                const float4 ikq = sIK4[0], ikq2 = sIK4[1];
+                const float rq0 = rc0 + fmaf(ikq.x, fq, ikq.y), rq1 = rc1 + fmaf(ikq.z, fq, ikq.w);
+                const float rq2 = rc2 + fmaf(ikq2.x, fq, ikq2.y);
+                const float Xq0 = Dq * rq0, Xq1 = Dq * rq1, Xq2 = Dq * rq2;
+                gP[0] = fma2(dc0, splat(Xq0), gP[0]); gP[1] = fma2(dc0, splat(Xq1), gP[1]);
+                gP[2] = fma2(dc0, splat(Xq2), gP[2]); gP[3] = add2(gP[3], dc0);
+                gP[4] = fma2(dc1, splat(Xq0), gP[4]); gP[5] = fma2(dc1, splat(Xq1), gP[5]);
+                gP[6] = fma2(dc1, splat(Xq2), gP[6]); gP[7] = add2(gP[7], dc1);
+                gP[8] = fma2(dc2, splat(Xq0), gP[8]); gP[9] = fma2(dc2, splat(Xq1), gP[9]);
+                gP[10] = fma2(dc2, splat(Xq2), gP[10]); gP[11] = add2(gP[11], dc2);
+                // gX = P[:, :3]^T dc
+                const float4 pa0 = sP4[0], pa1 = sP4[1], pb0 = sP4[2], pb1 = sP4[3], pc0 = sP4[4], pc1 = sP4[5];
+                const float2 gX0 = fma2(f2(pa0.x, pa0.y), dc0, fma2(f2(pb0.x, pb0.y), dc1, mul2(f2(pc0.x, pc0.y), dc2)));
+                const float2 gX1 = fma2(f2(pa0.z, pa0.w), dc0, fma2(f2(pb0.z, pb0.w), dc1, mul2(f2(pc0.z, pc0.w), dc2)));
+                const float2 gX2 = fma2(f2(pa1.x, pa1.y), dc0, fma2(f2(pb1.x, pb1.y), dc1, mul2(f2(pc1.x, pc1.y), dc2)));
+                const float2 gD = fma2(splat(rq0), gX0, fma2(splat(rq1), gX1, mul2(splat(rq2), gX2)));
+                g_d = -p.disp_range * Dq * Dq * (gD.x + gD.y);   // d(1/sigma)/d disp, both frames
+            }
+            if (do_q) {
+                if (kk > 1) {
+                    const float sy = fmaxf(fmaf(rscale, (float)qy + 0.5f, -0.5f), 0.f);
+                    const int i0 = (int)sy;
+                    const float mu = sy - (float)i0;
+                    if (i0 > cur) {            // low-res row `cur` is complete (warp-uniform)
+                        flush_row(cur, acc0);
+                        acc0 = acc1; acc1 = 0.f; cur = i0;
+                    }
+                    if (i0 + 1 <= hd - 1) { acc0 = fmaf(1.f - mu, g_d, acc0); acc1 = fmaf(mu, g_d, acc1); }
+                    else acc0 += g_d;
+                } else if (col_owned && ps.grad_disp != nullptr) {
+                    atomicAdd(at(ps.grad_disp, bp + qy * W + cx), g_d);   // RED: fire and forget
+                }
+            }
+        }
+        // ---- bilinear interpolation of row r (trainer.py:508) and its slopes ----
+        float2 xv[3], dpx[3], dpy[3];
+        float2 l1_cur = splat(0.f);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float2 dt = sub2(ne[c], nw[c]), db = sub2(se[c], sw[c]);
+            const float2 top = fma2(tx, dt, nw[c]), bot = fma2(tx, db, sw[c]);
             const float2 dvert = sub2(bot, top);
             xv[c] = fma2(ty, dvert, top);
             if (GRAD) {
@@ -459,91 +550,22 @@ sweep_kernel(const PhotoParams p) {
             }
         }
 
-        // ========================= (C) adjoint for the pixels of row r-2 =========================
+        // coefficients of window row r-1, consumed by the adjoint of the next step
         if (GRAD) {
-            const float2 wsc = mul2(wgt, splat(p.inv_n));      // winner weight of window row r-1
-            const int qy = r - 2;
-            const bool do_q = (r >= y0 + 2) && (qy < y1);      // y0 <= qy < y1
-            const float wt = (qy == 1) ? 2.f : 1.f, wb = (qy == H - 2) ? 2.f : 1.f;   // reflection fold (rows)
-            float2 V[9];
+            const float2 wsc = mul2(wgt, splat(p.inv_n));
             if (SSIM) {
                 const float2 base = mul2(wsc, splat(kssim9));
 #pragma unroll
                 for (int m = 0; m < 9; ++m) {
                     const int c = m % 3;
                     // d rp / d x_q = (0.85/27) * (pa + x_q pb + y_q pe) for q in the window of p
-                    const float2 cf = mul2(base, m < 3 ? pa[c] : (m < 6 ? pb[c] : pe[c]));
-                    const float2 cl = shfl_up2(cf), cr = shfl_down2(cf);
-                    const float2 hn = fma2(splat(wl), cl, fma2(splat(wr), cr, cf));
-                    V[m] = fma2(splat(wt), hcB[m], fma2(splat(wb), hn, hcA[m]));
-                    hcB[m] = hn;
+                    cfc[m] = mul2(base, m < 3 ? pa[c] : (m < 6 ? pb[c] : pe[c]));
                 }
             }
-            float g_d = 0.f;
-            if (do_q && col_owned) {
-                const float4* rc = sRing + (((slotA + 1) % 3) * kSweepRingQ) * 32 + lane;
-                const float4 q0r = rc[0 * 32], q1r = rc[1 * 32], q2r = rc[2 * 32], q3r = rc[3 * 32];
-                const float4 q4r = rc[4 * 32], q5r = rc[5 * 32], q6r = rc[6 * 32];
-                const float yq[3] = {q0r.x, q0r.y, q0r.z};
-                const float Dq = q0r.w;
-                const float2 xq[3] = {f2(q1r.x, q1r.y), f2(q1r.z, q1r.w), f2(q2r.x, q2r.y)};
-                const float2 dxq[3] = {f2(q2r.z, q2r.w), f2(q3r.x, q3r.y), f2(q3r.z, q3r.w)};
-                const float2 dyq[3] = {f2(q4r.x, q4r.y), f2(q4r.z, q4r.w), f2(q5r.x, q5r.y)};
-                const float2 invzq = f2(q5r.z, q5r.w), uq = f2(q6r.x, q6r.y), vq = f2(q6r.z, q6r.w);
-                const float2 kw = mul2(wq_prev, splat(kl1));   // wq_prev: winner weight of row r-2
-                float2 du = splat(0.f), dv = splat(0.f);
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float2 df = sub2(xq[c], splat(yq[c]));
-                    // d|x - y| / dx = sign(x - y).  sign(0) is taken as +1 instead of the reference's 0:
-                    // exact equality of a warped value and the target only happens on locally constant
-                    // images, where the bilinear slopes that multiply this term are exactly 0
-                    const float2 sg = f2(copysignf(kw.x, df.x), copysignf(kw.y, df.y));
-                    float2 g = sg;
-                    if (SSIM) g = add2(g, fma2(xq[c], V[3 + c], fma2(splat(yq[c]), V[6 + c], V[c])));
-                    du = fma2(g, dxq[c], du);
-                    dv = fma2(g, dyq[c], dv);
-                }
-                const float2 dc0 = mul2(du, invzq), dc1 = mul2(dv, invzq);
-                const float2 t = fma2(uq, du, mul2(vq, dv));
-                const float2 dc2 = mul2(f2(-t.x, -t.y), invzq);
-                const float fq = (float)qy;
-                const float4 ikq = sIK4[0], ikq2 = sIK4[1];
-                const float rq0 = rc0 + fmaf(ikq.x, fq, ikq.y), rq1 = rc1 + fmaf(ikq.z, fq, ikq.w);
-                const float rq2 = rc2 + fmaf(ikq2.x, fq, ikq2.y);
-                const float Xq0 = Dq * rq0, Xq1 = Dq * rq1, Xq2 = Dq * rq2;
-                gP[0] = fma2(dc0, splat(Xq0), gP[0]); gP[1] = fma2(dc0, splat(Xq1), gP[1]);
-                gP[2] = fma2(dc0, splat(Xq2), gP[2]); gP[3] = add2(gP[3], dc0);
-                gP[4] = fma2(dc1, splat(Xq0), gP[4]); gP[5] = fma2(dc1, splat(Xq1), gP[5]);
-                gP[6] = fma2(dc1, splat(Xq2), gP[6]); gP[7] = add2(gP[7], dc1);
-                gP[8] = fma2(dc2, splat(Xq0), gP[8]); gP[9] = fma2(dc2, splat(Xq1), gP[9]);
-                gP[10] = fma2(dc2, splat(Xq2), gP[10]); gP[11] = add2(gP[11], dc2);
-                // gX = P[:, :3]^T dc
-                const float4 pa0 = sP4[0], pa1 = sP4[1], pb0 = sP4[2], pb1 = sP4[3], pc0 = sP4[4], pc1 = sP4[5];
-                const float2 gX0 = fma2(f2(pa0.x, pa0.y), dc0, fma2(f2(pb0.x, pb0.y), dc1, mul2(f2(pc0.x, pc0.y), dc2)));
-                const float2 gX1 = fma2(f2(pa0.z, pa0.w), dc0, fma2(f2(pb0.z, pb0.w), dc1, mul2(f2(pc0.z, pc0.w), dc2)));
-                const float2 gX2 = fma2(f2(pa1.x, pa1.y), dc0, fma2(f2(pb1.x, pb1.y), dc1, mul2(f2(pc1.x, pc1.y), dc2)));
-                const float2 gD = fma2(splat(rq0), gX0, fma2(splat(rq1), gX1, mul2(splat(rq2), gX2)));
-                g_d = -p.disp_range * Dq * Dq * (gD.x + gD.y);   // d(1/sigma)/d disp, both frames
-            }
-            wq_prev = wsc;
-            if (do_q) {
-                if (kk > 1) {
-                    const float sy = fmaxf(fmaf(rscale, (float)qy + 0.5f, -0.5f), 0.f);
-                    const int i0 = (int)sy;
-                    const float mu = sy - (float)i0;
-                    if (i0 > cur) {            // low-res row `cur` is complete (warp-uniform)
-                        flush_row(cur, acc0);
-                        acc0 = acc1; acc1 = 0.f; cur = i0;
-                    }
-                    if (i0 + 1 <= hd - 1) { acc0 = fmaf(1.f - mu, g_d, acc0); acc1 = fmaf(mu, g_d, acc1); }
-                    else acc0 += g_d;
-                } else if (col_owned && ps.grad_disp != nullptr) {
-                    atomicAdd(at(ps.grad_disp, bp + qy * W + cx), g_d);   // RED: fire and forget
-                }
-            }
+            wq2 = wq1;
+            wq1 = wsc;
         }
-        slotA = (slotA + 1 == 3) ? 0 : slotA + 1;
+        slotA = (slotA + 1) & 3;
     };
     // Always an even number of steps: a possible extra step past r_end only evaluates rows nobody
     // owns (no emission, do_q false), and keeps the unrolled loop free of a conditional join.

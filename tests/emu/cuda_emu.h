@@ -1,14 +1,14 @@
 // TEST INFRASTRUCTURE ONLY -- never linked into libpml.so, never imported by the package.
 //
 // A tiny SPMD emulator that lets g++ compile the *same* kernel sources as nvcc
-// (self-supervised-depth-estimation_b200/csrc/*.cuh) and run them on host threads: one OS thread
-// per CUDA thread of a block, blocks executed one after another.  The build container has no
+// (self-supervised-depth-estimation_b200/csrc/*.cuh) and run them on the host: one user-level fiber
+// per CUDA thread of a block, blocks spread over a pool of OS threads.  The build container has no
 // GPU, so this is how kernel logic is debugged before GPU minutes are spent; the parity that
-// counts is still measured on the B200 (tests marked `gpu`).  __syncthreads maps to a
-// std::barrier, warp shuffles to a per-warp exchange buffer, atomics to std::atomic_ref.
+// counts is still measured on the B200 (tests marked `gpu`).  __syncthreads / __syncwarp are fiber
+// yields until the group has arrived, warp shuffles a per-warp exchange buffer, atomics std::atomic_ref.
 #pragma once
 #include <atomic>
-#include <barrier>
+#include <ucontext.h>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -26,7 +26,7 @@
 #define __forceinline__ inline
 #define __noinline__
 #define __launch_bounds__(...)
-#define __shared__ static
+#define __shared__ static thread_local   /* one block at a time per OS thread */
 #define __align__(n)
 #define __restrict__ __restrict
 
@@ -42,46 +42,109 @@ typedef int cudaError_t;
 enum { cudaSuccess = 0 };
 
 namespace emu {
-struct Block {
-    unsigned nthreads;
-    std::barrier<>* bar;
-    std::vector<std::unique_ptr<std::barrier<>>>* warp_bars;
-    std::vector<uint32_t>* warp_xchg;   // [nwarps][32]
-    std::vector<unsigned char>* smem;
+// Execution model: every CUDA thread of a block is a user-level fiber (ucontext) of ONE OS thread,
+// scheduled round-robin; a barrier / shuffle is a fiber yield (~100 ns) instead of an OS-level
+// rendezvous.  Blocks are independent and run in parallel on a small pool of OS threads.
+struct Group { unsigned size = 0, count = 0, gen = 0; };
+struct Lane {
+    ucontext_t ctx;
+    std::vector<unsigned char> stack;
+    uint3_ tid;
+    bool done = false;
 };
-inline thread_local uint3_ t_threadIdx, t_blockIdx, t_blockDim, t_gridDim;
+struct Block {
+    unsigned nthreads = 0;
+    uint3_ bid, bdim, gdim;
+    std::vector<Lane> lanes;
+    Group all;
+    std::vector<Group> warps;
+    std::vector<uint32_t> warp_xchg;   // [nwarps][32]
+    std::vector<unsigned char> smem;
+    ucontext_t sched;
+    unsigned cur = 0;
+    const std::function<void()>* body = nullptr;
+};
 inline thread_local Block* t_block = nullptr;
+inline thread_local uint3_ t_threadIdx, t_blockIdx, t_blockDim, t_gridDim;
+
+inline void yield_to_scheduler() {
+    Block* b = t_block;
+    swapcontext(&b->lanes[b->cur].ctx, &b->sched);
+}
+inline void group_wait(Group& g) {
+    const unsigned my = g.gen;
+    if (++g.count == g.size) { g.count = 0; ++g.gen; return; }
+    while (g.gen == my) yield_to_scheduler();
+}
+inline void lane_entry() {
+    Block* b = t_block;
+    (*b->body)();
+    b->lanes[b->cur].done = true;
+    swapcontext(&b->lanes[b->cur].ctx, &b->sched);
+}
+inline void run_block(Block& blk) {
+    t_block = &blk;
+    t_blockIdx = blk.bid; t_blockDim = blk.bdim; t_gridDim = blk.gdim;
+    unsigned live = blk.nthreads;
+    for (unsigned t = 0; t < blk.nthreads; ++t) {
+        Lane& l = blk.lanes[t];
+        l.done = false;
+        getcontext(&l.ctx);
+        l.ctx.uc_stack.ss_sp = l.stack.data();
+        l.ctx.uc_stack.ss_size = l.stack.size();
+        l.ctx.uc_link = &blk.sched;
+        makecontext(&l.ctx, (void (*)())lane_entry, 0);
+    }
+    while (live) {
+        for (unsigned t = 0; t < blk.nthreads; ++t) {
+            Lane& l = blk.lanes[t];
+            if (l.done) continue;
+            blk.cur = t;
+            t_threadIdx = l.tid;
+            swapcontext(&blk.sched, &l.ctx);
+            if (l.done) --live;
+        }
+    }
+}
 
 template <class F>
-void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& body) {
-    unsigned nt = block.x * block.y * block.z;
-    unsigned nwarps = (nt + 31) / 32;
-    for (unsigned bz = 0; bz < grid.z; ++bz)
-    for (unsigned by = 0; by < grid.y; ++by)
-    for (unsigned bx = 0; bx < grid.x; ++bx) {
-        std::barrier<> bar(nt);
-        std::vector<std::unique_ptr<std::barrier<>>> wb;
-        for (unsigned w = 0; w < nwarps; ++w) {
-            unsigned lanes = std::min(32u, nt - w * 32);
-            wb.emplace_back(new std::barrier<>(lanes));
-        }
-        std::vector<uint32_t> xchg(nwarps * 32);
-        std::vector<unsigned char> smem(smem_bytes + 64);
-        Block blk{nt, &bar, &wb, &xchg, &smem};
-        std::vector<std::thread> th;
-        th.reserve(nt);
+void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& body_in) {
+    const std::function<void()> body = body_in;
+    const unsigned nt = block.x * block.y * block.z;
+    const unsigned nwarps = (nt + 31) / 32;
+    const unsigned long long nblocks = (unsigned long long)grid.x * grid.y * grid.z;
+    unsigned nworkers = std::thread::hardware_concurrency();
+    if (nworkers == 0) nworkers = 4;
+    if (nworkers > 16) nworkers = 16;
+    if (nworkers > nblocks) nworkers = (unsigned)nblocks;
+    std::atomic<unsigned long long> next{0};
+    auto worker = [&]() {
+        Block blk;
+        blk.nthreads = nt;
+        blk.bdim = {block.x, block.y, block.z};
+        blk.gdim = {grid.x, grid.y, grid.z};
+        blk.lanes.resize(nt);
         for (unsigned t = 0; t < nt; ++t) {
-            th.emplace_back([&, t]() {
-                t_threadIdx = {t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
-                t_blockIdx = {bx, by, bz};
-                t_blockDim = {block.x, block.y, block.z};
-                t_gridDim = {grid.x, grid.y, grid.z};
-                t_block = &blk;
-                body();
-            });
+            blk.lanes[t].stack.resize(256 * 1024);
+            blk.lanes[t].tid = {t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
         }
-        for (auto& x : th) x.join();
-    }
+        blk.warps.resize(nwarps);
+        blk.warp_xchg.resize(nwarps * 32);
+        blk.smem.resize(smem_bytes + 64);
+        blk.body = &body;
+        for (;;) {
+            const unsigned long long i = next.fetch_add(1);
+            if (i >= nblocks) break;
+            blk.bid = {(unsigned)(i % grid.x), (unsigned)((i / grid.x) % grid.y), (unsigned)(i / ((unsigned long long)grid.x * grid.y))};
+            blk.all = Group{nt, 0, 0};
+            for (unsigned w = 0; w < nwarps; ++w) blk.warps[w] = Group{std::min(32u, nt - w * 32), 0, 0};
+            run_block(blk);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned w = 1; w < nworkers; ++w) pool.emplace_back(worker);
+    worker();
+    for (auto& t : pool) t.join();
 }
 inline unsigned linear_tid() {
     return t_threadIdx.x + t_blockDim.x * (t_threadIdx.y + t_blockDim.y * t_threadIdx.z);
@@ -93,17 +156,15 @@ inline unsigned linear_tid() {
 #define blockDim (emu::t_blockDim)
 #define gridDim (emu::t_gridDim)
 
-static inline void __syncthreads() { emu::t_block->bar->arrive_and_wait(); }
-static inline void __syncwarp(unsigned = 0xffffffffu) {
-    (*emu::t_block->warp_bars)[emu::linear_tid() / 32]->arrive_and_wait();
-}
+static inline void __syncthreads() { emu::group_wait(emu::t_block->all); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { emu::group_wait(emu::t_block->warps[emu::linear_tid() / 32]); }
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 
 template <class T>
 static inline T emu_shfl(T v, unsigned src_lane) {
     static_assert(sizeof(T) == 4, "32-bit shuffles only");
     unsigned tid = emu::linear_tid(), w = tid / 32, lane = tid % 32;
-    uint32_t* buf = emu::t_block->warp_xchg->data() + w * 32;
+    uint32_t* buf = emu::t_block->warp_xchg.data() + w * 32;
     uint32_t bits;
     std::memcpy(&bits, &v, 4);
     buf[lane] = bits;
@@ -173,4 +234,4 @@ enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 #define PML_LAUNCH(kernel, grid, block, smem, stream, ...) \
     emu::launch((grid), (block), (smem), [&]() { kernel(__VA_ARGS__); })
 #define PML_DYN_SMEM(type, name) \
-    type* name = reinterpret_cast<type*>((reinterpret_cast<uintptr_t>(emu::t_block->smem->data()) + 15) & ~uintptr_t(15))
+    type* name = reinterpret_cast<type*>((reinterpret_cast<uintptr_t>(emu::t_block->smem.data()) + 15) & ~uintptr_t(15))
