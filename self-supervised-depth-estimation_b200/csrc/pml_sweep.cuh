@@ -262,8 +262,8 @@ sweep_kernel(const PhotoParams p) {
 
     // Streaming inputs of one row, issued one row step before they are consumed: target colours and
     // the (up to four) disparity values around (rx, ry).
-    float yn[3], dn[4];
-    auto load_row = [&](int r) {
+    float ynA[3], dnA[4], ynB[3], dnB[4];
+    auto load_row = [&](int r, float (&yn)[3], float (&dn)[4]) {
         const int ry = reflect1(clampi(r, -1, H), H);
         const float* tq = at(tgt_g, b3p + ry * W + rx);
         yn[0] = __ldg(tq); yn[1] = __ldg(at(tq, plane)); yn[2] = __ldg(at(tq, 2 * plane));
@@ -277,19 +277,19 @@ sweep_kernel(const PhotoParams p) {
             dn[0] = __ldg(at(disp_g, bdp + ry * W + rx));
         }
     };
-    load_row(y0 - 2);
+    load_row(y0 - 2, ynA, dnA);
 
     int slotA = 0;   // ring slot of row r; slot (slotA + 1) & 3 holds row r-3
     const int r_end = GRAD ? (y1 + 2) : y1;
     // One row step.  The rolling 3x3 sums are passed as (previous row, row before): the step reads
     // both and overwrites the older one, so calling it with the two sets swapped on alternate rows
     // (loop unrolled by two below) rotates the window without a single register move.
-    auto step = [&](const int r, float (&hyA)[3], float (&hyB)[3], float (&hyyA)[3], float (&hyyB)[3],
+    auto step = [&](const int r, const float (&yv)[3], const float (&dn)[4], float (&ynN)[3], float (&dnN)[4],
+                    float (&hyA)[3], float (&hyB)[3], float (&hyyA)[3], float (&hyyB)[3],
                     float2 (&hxA)[3], float2 (&hxB)[3], float2 (&hxxA)[3], float2 (&hxxB)[3],
                     float2 (&hxyA)[3], float2 (&hxyB)[3], float2 (&hcA)[GRAD ? 9 : 1], float2 (&hcB)[GRAD ? 9 : 1]) {
         // =================================== (A) warp row r ======================================
         const int ry = reflect1(clampi(r, -1, H), H);
-        const float yv[3] = {yn[0], yn[1], yn[2]};
         float d;
         if (kk > 1) {   // bilinear upsample of disp_s, align_corners=False (trainer.py:474)
             const float sy = fmaxf(fmaf(rscale, (float)ry + 0.5f, -0.5f), 0.f);
@@ -299,7 +299,7 @@ sweep_kernel(const PhotoParams p) {
         } else {
             d = dn[0];
         }
-        load_row(r + 1);   // consumed by the next step
+        load_row(r + 1, ynN, dnN);   // consumed by the next step
         // identity losses / noise of the window row r-1 (used at the end of (B)); clamped so that the
         // early, unconditional loads stay inside the tensors
         const int py = r - 1;
@@ -348,17 +348,16 @@ sweep_kernel(const PhotoParams p) {
         const float2 my = f2((iyr.x > 0.f && iyr.x < hmax) ? hscale : 0.f, (iyr.y > 0.f && iyr.y < hmax) ? hscale : 0.f);
         // address of the north-west tap; the other taps are warp-uniform offsets (plane, W) from it,
         // or the immediate +1
-        const float* q0 = at(src0_g, b3p + (int)fy0.x * W + (int)fx0.x);
-        const float* q1 = at(src1_g, b3p + (int)fy0.y * W + (int)fx0.y);
+        const int o0 = b3p + (int)fy0.x * W + (int)fx0.x, o1 = b3p + (int)fy0.y * W + (int)fx0.y;
 
         // ---- issue the 24 taps of row r; they are consumed after the adjoint below ----
         float2 nw[3], ne[3], sw[3], se[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const float* a0 = (c == 0) ? q0 : at(q0, c * plane);
-            const float* a1 = (c == 0) ? q1 : at(q1, c * plane);
-            const float* w0 = at(q0, c * plane + W);
-            const float* w1 = at(q1, c * plane + W);
+            const float* a0 = at(src0_g, o0 + c * plane);
+            const float* a1 = at(src1_g, o1 + c * plane);
+            const float* w0 = at(src0_g, o0 + (c * plane + W));
+            const float* w1 = at(src1_g, o1 + (c * plane + W));
             nw[c] = f2(__ldg(a0), __ldg(a1)); ne[c] = f2(__ldg(a0 + 1), __ldg(a1 + 1));
             sw[c] = f2(__ldg(w0), __ldg(w1)); se[c] = f2(__ldg(w0 + 1), __ldg(w1 + 1));
         }
@@ -380,8 +379,10 @@ sweep_kernel(const PhotoParams p) {
                     hcB[m] = hn;
                 }
             }
-            float g_d = 0.f;
-            if (do_q && col_owned) {
+            float g_d;
+            {   // straight-line for every lane (no divergent join): lanes / rows that own nothing read
+                // whatever the ring holds and are masked where du / dv enter the sums
+                const bool own_q = do_q && col_owned;
                 const float4* rc = sRing + (((slotA + 1) & 3) * kSweepRingQ) * 32 + lane;
                 const float4 q0r = rc[0 * 32], q1r = rc[1 * 32], q2r = rc[2 * 32], q3r = rc[3 * 32];
                 const float4 q4r = rc[4 * 32], q5r = rc[5 * 32], q6r = rc[6 * 32];
@@ -405,6 +406,8 @@ sweep_kernel(const PhotoParams p) {
                     du = fma2(g, dxq[c], du);
                     dv = fma2(g, dyq[c], dv);
                 }
+                du = f2(own_q ? du.x : 0.f, own_q ? du.y : 0.f);
+                dv = f2(own_q ? dv.x : 0.f, own_q ? dv.y : 0.f);
                 const float2 dc0 = mul2(du, invzq), dc1 = mul2(dv, invzq);
                 const float2 t = fma2(uq, du, mul2(vq, dv));
                 const float2 dc2 = mul2(f2(-t.x, -t.y), invzq);
@@ -425,7 +428,7 @@ sweep_kernel(const PhotoParams p) {
                 const float2 gX1 = fma2(f2(pa0.z, pa0.w), dc0, fma2(f2(pb0.z, pb0.w), dc1, mul2(f2(pc0.z, pc0.w), dc2)));
                 const float2 gX2 = fma2(f2(pa1.x, pa1.y), dc0, fma2(f2(pb1.x, pb1.y), dc1, mul2(f2(pc1.x, pc1.y), dc2)));
                 const float2 gD = fma2(splat(rq0), gX0, fma2(splat(rq1), gX1, mul2(splat(rq2), gX2)));
-                g_d = -p.disp_range * Dq * Dq * (gD.x + gD.y);   // d(1/sigma)/d disp, both frames
+                g_d = own_q ? -p.disp_range * Dq * Dq * (gD.x + gD.y) : 0.f;   // d(1/sigma)/d disp, both frames
             }
             if (do_q) {
                 if (kk > 1) {
@@ -571,8 +574,8 @@ sweep_kernel(const PhotoParams p) {
     // owns (no emission, do_q false), and keeps the unrolled loop free of a conditional join.
 #pragma unroll 1
     for (int r = y0 - 2; r <= r_end; r += 2) {
-        step(r, hy1, hy2, hyy1, hyy2, hx1, hx2, hxx1, hxx2, hxy1, hxy2, hc1, hc2);
-        step(r + 1, hy2, hy1, hyy2, hyy1, hx2, hx1, hxx2, hxx1, hxy2, hxy1, hc2, hc1);
+        step(r, ynA, dnA, ynB, dnB, hy1, hy2, hyy1, hyy2, hx1, hx2, hxx1, hxx2, hxy1, hxy2, hc1, hc2);
+        step(r + 1, ynB, dnB, ynA, dnA, hy2, hy1, hyy2, hyy1, hx2, hx1, hxx2, hxx1, hxy2, hxy1, hc2, hc1);
     }
 
     // ------------------------------------ epilogue ------------------------------------------------
