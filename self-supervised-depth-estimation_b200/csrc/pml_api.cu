@@ -3,6 +3,7 @@
 #include "pml_common.cuh"
 #include "pml_photometric.cuh"
 #include "pml_sweep.cuh"
+#include "pml_prep.cuh"
 #include "pml_smooth.cuh"
 #include "pml_layers.cuh"
 
@@ -108,7 +109,9 @@ Plan make_plan(const pml_problem* p, bool grad) {
     pl.n_id = automask ? (avg ? 1 : p->S) : 0;
     pl.smooth_total = 0;
     for (int i = 0; i < p->n_pass; ++i) {
-        pl.smooth_blocks[i] = (p->pass[i].hd * p->pass[i].wd + 255) / 256;
+        pl.smooth_blocks[i] = pl.sweep ? ((p->pass[i].wd + pml::kPrepTW - 1) / pml::kPrepTW) *
+                                         ((p->pass[i].hd + pml::kSmoothTH - 1) / pml::kSmoothTH)
+                                       : (p->pass[i].hd * p->pass[i].wd + 255) / 256;
         pl.smooth_off[i] = pl.smooth_total;
         pl.smooth_total += pl.smooth_blocks[i] * p->B;
     }
@@ -195,11 +198,27 @@ int run_loss(const pml_problem* p, void* ws, size_t ws_bytes, cudaStream_t st, b
         sp.pass[i].weight = ps.smooth_weight;
     }
     PML_LAUNCH(disp_sum_kernel, dim3(pl.max_chunks, p->B, p->n_pass), dim3(256), 0, st, sp);
-    if (grad) PML_LAUNCH(smooth_kernel<true>, dim3(pl.smooth_total), dim3(256), 0, st, sp);
-    else      PML_LAUNCH(smooth_kernel<false>, dim3(pl.smooth_total), dim3(256), 0, st, sp);
+    if (pl.sweep) {
+        if (grad) PML_LAUNCH(smooth_sweep_kernel<true>, dim3(pl.smooth_total), dim3(32), 0, st, sp);
+        else      PML_LAUNCH(smooth_sweep_kernel<false>, dim3(pl.smooth_total), dim3(32), 0, st, sp);
+    } else {
+        if (grad) PML_LAUNCH(smooth_kernel<true>, dim3(pl.smooth_total), dim3(256), 0, st, sp);
+        else      PML_LAUNCH(smooth_kernel<false>, dim3(pl.smooth_total), dim3(256), 0, st, sp);
+    }
 
     // 3. identity reprojection losses (automask), once for all passes
-    if (pl.n_id > 0) {
+    if (pl.n_id > 0 && pl.sweep) {
+        IdentityParams ip;
+        ip.target = p->target; ip.src0 = p->sources[0]; ip.src1 = p->sources[p->S > 1 ? 1 : 0];
+        ip.out = identity; ip.B = p->B; ip.H = p->H; ip.W = p->W; ip.S = p->S;
+        ip.avg = (p->flags & PML_FLAG_AVG_REPROJ) ? 1 : 0;
+        ip.TH = env_int("PML_ID_TH", 16);
+        ip.n_strips = (p->W + kPrepTW - 1) / kPrepTW;
+        ip.n_chunks = (p->H + ip.TH - 1) / ip.TH;
+        const dim3 g(ip.n_chunks * ip.n_strips, p->B);
+        if (ssim) PML_LAUNCH(identity_sweep_kernel<true>, g, dim3(32), 0, st, ip);
+        else      PML_LAUNCH(identity_sweep_kernel<false>, g, dim3(32), 0, st, ip);
+    } else if (pl.n_id > 0) {
         dim3 g((p->W + 255) / 256, p->H, p->B);
         const int avg = (p->flags & PML_FLAG_AVG_REPROJ) ? 1 : 0;
         if (ssim) PML_LAUNCH(identity_kernel<true>, g, dim3(256), 0, st, p->target, p->sources[0], p->sources[1],
@@ -254,7 +273,7 @@ int run_loss(const pml_problem* p, void* ws, size_t ws_bytes, cudaStream_t st, b
     }
     fq.losses = p->losses; fq.grad_T = p->grad_T; fq.grad_disp_const = p->grad_disp_const;
     fq.image_part = imagepart;
-    PML_LAUNCH(finalize_image_kernel, dim3(p->B, p->n_pass), dim3(128), 0, st, fq);
+    PML_LAUNCH(finalize_image_kernel, dim3(p->B, p->n_pass), dim3(256), 0, st, fq);
     PML_LAUNCH(finalize_loss_kernel, dim3(p->n_pass), dim3(32), 0, st, fq);
     return cudaGetLastError() == cudaSuccess ? PML_OK : PML_ERR_CUDA;
 }

@@ -137,6 +137,7 @@ class _PhotometricLoss(torch.autograd.Function):
 
         ctx.want_grad = want_grad
         ctx.cfg = cfg
+        ctx.set_materialize_grads(False)   # no zero-filled grads for the non-differentiable by-products
         if want_grad:
             ctx.gdisps, ctx.grad_T, ctx.grad_const = gdisps, grad_T, grad_const
             ctx.shapes = [(d.shape[2], d.shape[3]) for d in disps]
@@ -151,7 +152,7 @@ class _PhotometricLoss(torch.autograd.Function):
     def backward(ctx, g_loss, *unused):
         n_pass, S = ctx.cfg["n_pass"], ctx.cfg["S"]
         n_in = len(ctx.needs_input_grad)
-        if not ctx.want_grad:
+        if not ctx.want_grad or g_loss is None:
             return (None,) * n_in
         if ctx.consumed:
             raise RuntimeError("libpml photometric-loss gradients were already consumed in place by a previous "
