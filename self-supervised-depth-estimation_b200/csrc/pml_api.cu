@@ -4,6 +4,7 @@
 #include "pml_photometric.cuh"
 #include "pml_sweep.cuh"
 #include "pml_prep.cuh"
+#include "pml_pipe.cuh"
 #include "pml_smooth.cuh"
 #include "pml_layers.cuh"
 
@@ -155,7 +156,10 @@ int launch_sweep(const PhotoParams& pp, cudaStream_t st) {
     const size_t smem = sweep_smem_bytes();   // < 48 KB: no opt-in needed
     if (pp.B > 65535) return PML_ERR_UNSUPPORTED;
     const dim3 grid(pp.n_chunks * pp.n_strips, pp.B, pp.n_pass);
-    PML_LAUNCH((sweep_kernel<GRAD, SSIM>), grid, dim3(kSweepWarps * 32), smem, st, pp);
+    // PML_KERNEL=pipe: three-stage warp-specialised pipeline (pml_pipe.cuh) instead of the single-warp sweep
+    static const bool pipe = [] { const char* k = getenv("PML_KERNEL"); return k && k[0] == 'p'; }();
+    if (pipe) PML_LAUNCH((pipe_kernel<GRAD, SSIM>), grid, dim3(96), pipe_smem_bytes(), st, pp);
+    else      PML_LAUNCH((sweep_kernel<GRAD, SSIM>), grid, dim3(kSweepWarps * 32), smem, st, pp);
     return PML_OK;
 }
 
