@@ -252,23 +252,47 @@ def run_ours(args, rank, world, dev):
             host.append((hi, ho))
         h2d = sum(v.numel() * v.element_size() for v in list(host[0][0].values()) + list(host[0][1].values()))
 
-        def e2e_step(hi, ho):
-            inp = {k: v.to(dev, non_blocking=True) for k, v in hi.items()}
-            out = {k: v.to(dev, non_blocking=True) for k, v in ho.items()}
+        # Double-buffered like a DataLoader with pin_memory: the H2D copies of step i+1 run on a copy
+        # stream while the kernels of step i run on the compute stream.  Every step still uploads its
+        # own inputs from pinned host memory and reads its loss back inside the timed region.
+        copy_stream = torch.cuda.Stream(device=dev)
+        main_stream = torch.cuda.current_stream(dev)
+
+        def upload(hi, ho):
+            with torch.cuda.stream(copy_stream):
+                inp = {k: v.to(dev, non_blocking=True) for k, v in hi.items()}
+                out = {k: v.to(dev, non_blocking=True) for k, v in ho.items()}
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return inp, out, ev
+
+        def compute(inp, out, ev):
+            main_stream.wait_event(ev)
+            for v in list(inp.values()) + list(out.values()):
+                v.record_stream(main_stream)
             for k, v in out.items():
                 v.requires_grad_(True)
             trainer_hooks.generate_images_pred(ns, inp, out)
             losses = trainer_hooks.compute_losses(ns, inp, out)
             losses["loss"].backward()
-            return losses["loss"].item()   # D2H read of the step's result
+            return losses["loss"]
+
+        def run_steps(n):
+            nxt = upload(*host[0])
+            last = None
+            for i in range(n):
+                cur = nxt
+                if i + 1 < n:
+                    nxt = upload(*host[(i + 1) % len(host)])
+                loss = compute(*cur)
+                last = loss.item()   # D2H read of the step's result
+            return last
 
         Ke = max(3, min(K, 50))
-        for i in range(3):
-            e2e_step(*host[i % len(host)])
+        run_steps(3)
         barrier()
         t0 = time.perf_counter()
-        for i in range(Ke):
-            e2e_step(*host[i % len(host)])
+        run_steps(Ke)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], device=dev)
@@ -277,7 +301,8 @@ def run_ours(args, rank, world, dev):
         e2e = {"value": round(world * n_pix * Ke / t.item() / 1e6, 2), "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4, "steps": Ke,
                "ms_per_step": round(t.item() / Ke * 1e3, 4),
-               "api": "trainer_hooks.generate_images_pred + compute_losses + loss.backward()"}
+               "api": "trainer_hooks.generate_images_pred + compute_losses + loss.backward(); pinned-host inputs, "
+                      "H2D of step i+1 overlapped with the kernels of step i (copy stream), loss.item() every step"}
 
     res = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
            "ms_per_step": round(ms_total / K, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -90,9 +90,10 @@ Plan make_plan(const pml_problem* p, bool grad) {
     if (pl.sweep) { pl.NT = pml::kSweepWarps * 32; pl.TW = pml::kSweepTW; }
     pl.n_strips = (p->W + pl.TW - 1) / pl.TW;
     // strip height: the tallest chunk that still yields ~6 CTAs per SM (4 halo rows per chunk);
-    // warp strips: ~3 waves of 8 resident warps per SM
+    // warp strips: ~1.5-2 waves of the 8 warps an SM holds (5 halo row steps per chunk; measured on
+    // B200 at the headline size: TH 96 beats 48 and 32)
     int per_chunk = p->n_pass * p->B * pl.n_strips;
-    int want = ((pl.sweep ? kNumSM * 8 * 3 : kNumSM * 6) + per_chunk - 1) / per_chunk;
+    int want = ((pl.sweep ? kNumSM * 12 : kNumSM * 6) + per_chunk - 1) / per_chunk;
     if (want < 1) want = 1;
     int th = (p->H + want - 1) / want;
     if (th < 16) th = 16;
