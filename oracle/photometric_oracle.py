@@ -305,3 +305,33 @@ def run(opt, inputs, outputs, sources=(-1, 1), variant="trainer", noise=None, dt
         for name, leaf in leaves.items():
             res[name] = leaf.grad.detach() if leaf.grad is not None else torch.zeros_like(leaf)
     return res
+
+
+def compute_depth_errors(gt, pred):
+    """layers.py:251-269 -> (abs_rel, sq_rel, rmse, rmse_log, a1, a2, a3)."""
+    thresh = torch.max(gt / pred, pred / gt)
+    a1 = (thresh < 1.25).float().mean().to(gt.dtype)          # the reference averages these in fp32
+    a2 = (thresh < 1.25 ** 2).float().mean().to(gt.dtype)
+    a3 = (thresh < 1.25 ** 3).float().mean().to(gt.dtype)
+    rmse = torch.sqrt(((gt - pred) ** 2).mean())
+    rmse_log = torch.sqrt(((torch.log(gt) - torch.log(pred)) ** 2).mean())
+    abs_rel = torch.mean(torch.abs(gt - pred) / gt)
+    sq_rel = torch.mean((gt - pred) ** 2 / gt)
+    return abs_rel, sq_rel, rmse, rmse_log, a1, a2, a3
+
+
+def compute_depth_losses(depth_pred, depth_gt, dtype=torch.float64):
+    """trainer.py:624-652 restated: resize to the ground truth's resolution, clamp to [1e-3, 80],
+    mask = gt > 0 inside the Garg/Eigen crop (rows 153:371, columns 44:1197 of a 375x1242 map),
+    median scaling, clamp, compute_depth_errors.  -> tensor [7] in depth_metric_names order."""
+    depth_pred, depth_gt = depth_pred.to(dtype), depth_gt.to(dtype)
+    pred = torch.clamp(F.interpolate(depth_pred, list(depth_gt.shape[2:]), mode="bilinear", align_corners=False), 1e-3, 80)
+    mask = depth_gt > 0
+    crop = torch.zeros_like(mask)
+    crop[:, :, 153:371, 44:1197] = 1
+    mask = mask * crop
+    gt = depth_gt[mask]
+    pred = pred[mask]
+    pred = pred * (torch.median(gt) / torch.median(pred))
+    pred = torch.clamp(pred, min=1e-3, max=80)
+    return torch.stack(compute_depth_errors(gt, pred))

@@ -140,3 +140,13 @@ def run(opt, inputs, outputs, variant="trainer", noise_seed=0, dtype=torch.float
         for name, leaf in leaves.items():
             res[name] = leaf.grad.detach() if leaf.grad is not None else torch.zeros_like(leaf)
     return res
+
+
+def run_depth_losses(depth_pred, depth_gt, dtype=torch.float32):
+    """Execute the reference's Trainer.compute_depth_losses (trainer.py:624-652) unbound."""
+    import numpy as np
+    mod, _ = load("trainer")
+    ns = SimpleNamespace(depth_metric_names=["de/abs_rel", "de/sq_rel", "de/rms", "de/log_rms", "da/a1", "da/a2", "da/a3"])
+    losses = {}
+    mod.Trainer.compute_depth_losses(ns, {"depth_gt": depth_gt.to(dtype)}, {("depth", 0, 0): depth_pred.to(dtype)}, losses)
+    return torch.tensor([float(np.asarray(losses[k])) for k in ns.depth_metric_names], dtype=torch.float64)

@@ -7,6 +7,7 @@
 #include "pml_pipe.cuh"
 #include "pml_smooth.cuh"
 #include "pml_layers.cuh"
+#include "pml_metrics.cuh"
 
 #include <stdlib.h>
 #include <atomic>

@@ -383,3 +383,47 @@ class _Pose(torch.autograd.Function):
         lib.check(lib.pml_pose_bwd(_ptr(aa), _ptr(tr), _ptr(gT), _ptr(ga), _ptr(gt), aa.shape[0], 1 if invert else 0,
                                    _stream_ptr(aa)), "pml_pose_bwd")
         return ga.reshape(sa), gt.reshape(st), None
+
+
+# ------------------------------------------------------------------------------------------------
+# monitoring metrics (trainer.py:624-652, layers.py:251-269)
+# ------------------------------------------------------------------------------------------------
+GARG_CROP_375x1242 = (153, 371, 44, 1197)   # trainer.py:641: crop_mask[:, :, 153:371, 44:1197] = 1
+
+
+def depth_metrics(depth_pred: torch.Tensor, depth_gt: torch.Tensor, crop=GARG_CROP_375x1242,
+                  min_depth: float = 1e-3, max_depth: float = 80.0) -> torch.Tensor:
+    """``Trainer.compute_depth_losses`` without its Python glue: depth_pred [B,1,H,W] (any
+    resolution), depth_gt [B,1,Hg,Wg] (0 = no measurement) -> 7 floats on the device in the order of
+    ``depth_metric_names``: abs_rel, sq_rel, rmse, rmse_log, a1, a2, a3.
+
+    Resize + clamp + mask + crop run in one kernel, median scaling + the seven error sums in a
+    second one; the two medians in between are taken with torch.sort on the device (a library
+    selection, like the reference's torch.median).  No host synchronisation."""
+    lib = get_library()
+    depth_pred = _check(depth_pred.detach(), "depth_pred", lib)
+    depth_gt = _check(depth_gt, "depth_gt", lib)
+    if depth_pred.dim() != 4 or depth_gt.dim() != 4 or depth_pred.shape[1] != 1 or depth_gt.shape[1] != 1 \
+            or depth_pred.shape[0] != depth_gt.shape[0]:
+        raise ValueError("depth_pred [B,1,H,W] and depth_gt [B,1,Hg,Wg] expected")
+    B, _, H, W = depth_pred.shape
+    _, _, Hg, Wg = depth_gt.shape
+    dev = depth_pred.device
+    n = B * Hg * Wg
+    pred = torch.empty(n, device=dev, dtype=torch.float32)
+    gt = torch.empty(n, device=dev, dtype=torch.float32)
+    count = torch.empty(1, device=dev, dtype=torch.int32)
+    cy0, cy1, cx0, cx1 = crop
+    st = _stream_ptr(depth_pred)
+    lib.check(lib.pml_depth_metrics_prepare(_ptr(depth_pred), _ptr(depth_gt), _ptr(pred), _ptr(gt), _ptr(count),
+                                            B, H, W, Hg, Wg, cy0, cy1, cx0, cx1, float(min_depth), float(max_depth), st),
+              "pml_depth_metrics_prepare")
+    # torch.median == lower middle element == sorted[(n_valid - 1) // 2]; masked entries are +inf
+    k = ((count.to(torch.int64) - 1).clamp_(min=0)) // 2
+    ratio = (torch.sort(gt).values[k] / torch.sort(pred).values[k]).to(torch.float32).contiguous()   # trainer.py:645
+    out = torch.empty(7, device=dev, dtype=torch.float32)
+    nb = lib.pml_depth_metrics_workspace_bytes()
+    ws = torch.empty(nb, device=dev, dtype=torch.uint8)
+    lib.check(lib.pml_depth_metrics_reduce(_ptr(pred), _ptr(gt), n, _ptr(ratio), _ptr(count), float(min_depth),
+                                           float(max_depth), _ptr(out), _ptr(ws), nb, st), "pml_depth_metrics_reduce")
+    return out

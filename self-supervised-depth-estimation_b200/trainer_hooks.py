@@ -3,6 +3,7 @@
     generate_images_pred(self, inputs, outputs)      trainer.py:465-515
     compute_reprojection_loss(self, pred, target)    trainer.py:517-529
     compute_losses(self, inputs, outputs) -> dict    trainer.py:531-622
+    compute_depth_losses(self, inputs, outputs, losses)   trainer.py:624-652 (monitoring metrics)
 
 and their copies in trainer_fusion.py:421-579, trainer_fusion_v3.py:447-590 and
 trainer_gru.py:864-1023 (4-tuple sequence keys).  ``install(trainer_module)`` monkey-patches a
@@ -181,6 +182,20 @@ def compute_losses(self, inputs, outputs):
     return losses
 
 
+DEPTH_METRIC_NAMES = ["de/abs_rel", "de/sq_rel", "de/rms", "de/log_rms", "da/a1", "da/a2", "da/a3"]   # trainer.py:121-122
+
+
+def compute_depth_losses(self, inputs, outputs, losses):
+    """trainer.py:624-652: monitoring metrics of ``outputs[("depth", 0, 0)]`` against
+    ``inputs["depth_gt"]`` (resize to the ground truth's resolution, clamp, Garg/Eigen crop, median
+    scaling, seven error measures), written into ``losses`` as numpy scalars like the reference."""
+    import numpy as np
+    names = getattr(self, "depth_metric_names", DEPTH_METRIC_NAMES)
+    vals = _F.depth_metrics(outputs[("depth", 0, 0)], inputs["depth_gt"]).cpu().numpy()
+    for i, metric in enumerate(names):
+        losses[metric] = np.array(vals[i])
+
+
 _VARIANTS = {"trainer": "trainer", "trainer_dpt": "trainer", "trainer_fusion": "fusion",
              "trainer_fusion_v3": "fusion_v3", "trainer_gru": "gru"}
 
@@ -206,6 +221,8 @@ def install(trainer_module, variant=None):
     cls.generate_images_pred = _gen
     cls.compute_reprojection_loss = compute_reprojection_loss
     cls.compute_losses = _loss
+    if hasattr(cls, "compute_depth_losses"):
+        cls.compute_depth_losses = compute_depth_losses
     for sym in ("BackprojectDepth", "Project3D", "SSIM", "disp_to_depth", "get_smooth_loss",
                 "transformation_from_parameters"):
         if hasattr(trainer_module, sym):

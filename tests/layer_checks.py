@@ -78,3 +78,29 @@ def run(device, B=2, H=16, W=24):
         (M64 * w.double()).sum().backward()
         assert err(M.detach().cpu(), M64.detach()) < 1e-6
         assert err(aa.grad.cpu(), aa64.grad) < 1e-4 and err(tr.grad.cpu(), tr64.grad) < 1e-5
+
+
+def depth_metrics(device):
+    """functional.depth_metrics / trainer_hooks.compute_depth_losses against the float64 oracle on the
+    reference-generated fixture (trainer.py:624-652)."""
+    import os
+    import numpy as np
+    from types import SimpleNamespace
+    from oracle import photometric_oracle as po
+    from ssde_b200 import functional as Fn, trainer_hooks
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "aux", "depth_metrics.npz"))
+    pred, gt = torch.from_numpy(z["pred"]), torch.from_numpy(z["gt"])
+    want = po.compute_depth_losses(pred, gt, torch.float64)
+    got = Fn.depth_metrics(pred.to(device), gt.to(device)).cpu().double()
+    rel = ((got - want).abs() / want.abs()).max().item()
+    assert rel < 2e-5, (got.tolist(), want.tolist())
+    assert torch.allclose(got, torch.from_numpy(z["ref_f64"]), rtol=2e-5, atol=0)      # the reference itself
+    # drop-in method: same dictionary entries as Trainer.compute_depth_losses
+    losses = {}
+    ns = SimpleNamespace(depth_metric_names=list(trainer_hooks.DEPTH_METRIC_NAMES))
+    trainer_hooks.compute_depth_losses(ns, {"depth_gt": gt.to(device)}, {("depth", 0, 0): pred.to(device)}, losses)
+    assert sorted(losses) == sorted(trainer_hooks.DEPTH_METRIC_NAMES)
+    assert abs(float(losses["de/abs_rel"]) - want[0].item()) / want[0].item() < 2e-5
+    # a ground truth at another resolution / with nothing inside the crop must not crash
+    empty = Fn.depth_metrics(pred.to(device), torch.zeros_like(gt).to(device)).cpu()
+    assert empty.shape == (7,)

@@ -63,6 +63,11 @@ def test_layer_dropins_match_oracle(emu_lib):
     layer_checks.run("cpu")
 
 
+def test_depth_metrics_match_oracle(emu_lib):
+    import layer_checks
+    layer_checks.depth_metrics("cpu")
+
+
 def test_host_rejects_bad_inputs(emu_lib):
     B, H, W = 1, 32, 64
     opt = synthetic.make_options(H, W, batch_size=B)

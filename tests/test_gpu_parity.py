@@ -117,6 +117,11 @@ def test_full_size_gradient_linearity(cuda_lib):
     assert common.rel_err(grads[1][1].cpu(), grads[0][1].cpu() * 2.5) < 1e-6
 
 
+def test_depth_metrics(cuda_lib):
+    import layer_checks
+    layer_checks.depth_metrics("cuda")
+
+
 def test_layer_dropins(cuda_lib):
     import layer_checks
     layer_checks.run("cuda")

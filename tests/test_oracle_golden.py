@@ -64,3 +64,17 @@ def test_unit_functions_closed_forms():
     assert po.smooth_loss(torch.ones(1, 1, 8, 8), torch.rand(1, 3, 8, 8, generator=g)).item() == 0
     s, dep = po.disp_to_depth(torch.tensor([0.0, 1.0]), 0.1, 100.0)
     assert torch.allclose(dep, torch.tensor([100.0, 0.1]))
+
+
+def test_depth_metrics_oracle_matches_reference():
+    """oracle.compute_depth_losses restates trainer.py:624-652 / layers.py:251-269; the fixture holds
+    the outputs of the unmodified reference (tests/golden/make_golden_depth.py)."""
+    import os
+    import numpy as np
+    from oracle import photometric_oracle as po
+    z = np.load(os.path.join(common.GOLDEN_DIR, "aux", "depth_metrics.npz"))
+    pred, gt = torch.from_numpy(z["pred"]), torch.from_numpy(z["gt"])
+    got64 = po.compute_depth_losses(pred, gt, torch.float64)
+    got32 = po.compute_depth_losses(pred, gt, torch.float32)
+    assert torch.allclose(got64, torch.from_numpy(z["ref_f64"]), rtol=1e-10, atol=0)
+    assert torch.allclose(got32.double(), torch.from_numpy(z["ref_f32"]), rtol=1e-6, atol=0)
