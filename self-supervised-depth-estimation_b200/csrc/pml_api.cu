@@ -26,7 +26,7 @@ struct Plan {
     int n_id;
     int smooth_blocks[PML_MAX_PASSES], smooth_off[PML_MAX_PASSES], smooth_total;
     int max_chunks;
-    size_t off_identity, off_part, off_mean, off_meanpart, off_imagepart, off_smooth, total;
+    size_t off_identity, off_part, off_mean, off_meanpart, off_imagepart, off_smooth, off_rp, off_argmin, total;
 };
 
 inline void pml_event_record(void* ev, cudaStream_t st) {
@@ -61,13 +61,16 @@ int validate(const pml_problem* p, bool grad) {
     return PML_OK;
 }
 
-// Which fused kernel serves this problem: the warp-strip sweep packs the two source frames of a
-// pixel into fp32x2 values (S <= 2); more source frames use the CTA-strip kernel.  PML_KERNEL=cta
-// forces the latter (A/B measurements).
+// Which fused kernel serves this problem.  The warp-strip sweep (pml_sweep.cuh) packs two source
+// frames of a pixel into fp32x2 values; four frames are swept pair by pair around a selection
+// kernel (2.0 ms vs 4.1 ms for the CTA-strip kernel at the headline size).  Three frames would leave
+// half of the second pair idle -- there the first-generation CTA-strip kernel (templated on S) is
+// still ahead (3.0 vs 3.4 ms at B=8, 320x1024) and is kept.  PML_KERNEL=cta / sweep force a choice.
 bool use_sweep(const pml_problem* p) {
     const char* k = getenv("PML_KERNEL");
     if (k && k[0] == 'c') return false;
-    return p->S <= 2;
+    if (k && (k[0] == 's' || k[0] == 'p')) return true;
+    return p->S != 3;
 }
 
 Plan make_plan(const pml_problem* p, bool grad) {
@@ -130,6 +133,12 @@ Plan make_plan(const pml_problem* p, bool grad) {
     pl.off_meanpart = off; off = align16(off + (size_t)p->n_pass * p->B * pl.max_chunks * sizeof(float));
     pl.off_imagepart = off; off = align16(off + (size_t)p->n_pass * p->B * 4 * sizeof(float));
     pl.off_smooth = off;   off = align16(off + (size_t)pl.smooth_total * 3 * sizeof(float));
+    pl.off_rp = pl.off_argmin = off;
+    if (pl.sweep && p->S > 2) {   // pair-by-pair sweep: reprojection losses of all frames + a selection map
+        off = align16(off + (size_t)p->n_pass * p->S * p->B * p->H * p->W * sizeof(float));
+        pl.off_argmin = off;
+        off = align16(off + (size_t)p->n_pass * p->B * p->H * p->W);
+    }
     pl.total = off;
     (void)grad;
     return pl;
@@ -160,7 +169,7 @@ int launch_sweep(const PhotoParams& pp, cudaStream_t st) {
     const dim3 grid(pp.n_chunks * pp.n_strips, pp.B, pp.n_pass);
     // PML_KERNEL=pipe: three-stage warp-specialised pipeline (pml_pipe.cuh) instead of the single-warp sweep
     static const bool pipe = [] { const char* k = getenv("PML_KERNEL"); return k && k[0] == 'p'; }();
-    if (pipe) PML_LAUNCH((pipe_kernel<GRAD, SSIM>), grid, dim3(96), pipe_smem_bytes(), st, pp);
+    if (pipe && pp.mode == 0 && pp.S <= 2) PML_LAUNCH((pipe_kernel<GRAD, SSIM>), grid, dim3(96), pipe_smem_bytes(), st, pp);
     else      PML_LAUNCH((sweep_kernel<GRAD, SSIM>), grid, dim3(kSweepWarps * 32), smem, st, pp);
     return PML_OK;
 }
@@ -214,16 +223,21 @@ int run_loss(const pml_problem* p, void* ws, size_t ws_bytes, cudaStream_t st, b
 
     // 3. identity reprojection losses (automask), once for all passes
     if (pl.n_id > 0 && pl.sweep) {
-        IdentityParams ip;
-        ip.target = p->target; ip.src0 = p->sources[0]; ip.src1 = p->sources[p->S > 1 ? 1 : 0];
-        ip.out = identity; ip.B = p->B; ip.H = p->H; ip.W = p->W; ip.S = p->S;
-        ip.avg = (p->flags & PML_FLAG_AVG_REPROJ) ? 1 : 0;
-        ip.TH = env_int("PML_ID_TH", 16);
-        ip.n_strips = (p->W + kPrepTW - 1) / kPrepTW;
-        ip.n_chunks = (p->H + ip.TH - 1) / ip.TH;
-        const dim3 g(ip.n_chunks * ip.n_strips, p->B);
-        if (ssim) PML_LAUNCH(identity_sweep_kernel<true>, g, dim3(32), 0, st, ip);
-        else      PML_LAUNCH(identity_sweep_kernel<false>, g, dim3(32), 0, st, ip);
+        for (int fa = 0; fa < p->S; fa += 2) {   // one launch per pair of source frames
+            IdentityParams ip;
+            const int pair_n = (fa + 1 < p->S) ? 2 : 1;
+            ip.target = p->target; ip.src0 = p->sources[fa]; ip.src1 = p->sources[fa + pair_n - 1];
+            ip.out = identity; ip.B = p->B; ip.H = p->H; ip.W = p->W; ip.S = pair_n;
+            ip.avg = (p->flags & PML_FLAG_AVG_REPROJ) ? 1 : 0;
+            ip.n_out = pl.n_id; ip.plane_off = ip.avg ? 0 : fa; ip.accumulate = (ip.avg && fa > 0) ? 1 : 0;
+            ip.inv_total = 1.0f / (float)p->S;
+            ip.TH = env_int("PML_ID_TH", 16);
+            ip.n_strips = (p->W + kPrepTW - 1) / kPrepTW;
+            ip.n_chunks = (p->H + ip.TH - 1) / ip.TH;
+            const dim3 g(ip.n_chunks * ip.n_strips, p->B);
+            if (ssim) PML_LAUNCH(identity_sweep_kernel<true>, g, dim3(32), 0, st, ip);
+            else      PML_LAUNCH(identity_sweep_kernel<false>, g, dim3(32), 0, st, ip);
+        }
     } else if (pl.n_id > 0) {
         dim3 g((p->W + 255) / 256, p->H, p->B);
         const int avg = (p->flags & PML_FLAG_AVG_REPROJ) ? 1 : 0;
@@ -254,10 +268,30 @@ int run_loss(const pml_problem* p, void* ws, size_t ws_bytes, cudaStream_t st, b
     }
     pp.TW = pl.TW; pp.TH = pl.TH; pp.n_strips = pl.n_strips; pp.n_chunks = pl.n_chunks;
     pp.n_items = pl.n_cta; pp.S = p->S;
+    pp.mode = 0; pp.f_base = 0; pp.pair_n = p->S > 1 ? 2 : 1; pp.rp = nullptr;
     pp.cta_per_pass = pl.cta_per_pass; pp.part = part; pp.part_stride = pl.part_stride;
     pp.inv_n = (float)(1.0 / ((double)p->B * p->H * p->W));
     if (p->prof_start) pml_event_record(p->prof_start, st);
-    if (pl.sweep) {
+    if (pl.sweep && p->S > 2) {
+        // More than two source frames: (1) forward sweep per frame pair -> reprojection losses,
+        // (2) selection over all candidates, (3) forward + adjoint sweep per pair with that selection.
+        pp.rp = reinterpret_cast<float*>(base + pl.off_rp);
+        for (int i = 0; i < p->n_pass; ++i)
+            if (!pp.pass[i].argmin)
+                pp.pass[i].argmin = reinterpret_cast<uint8_t*>(base + pl.off_argmin) + (size_t)i * p->B * p->H * p->W;
+        pp.mode = 1;
+        for (int fa = 0; fa < p->S && rc == PML_OK; fa += 2) {
+            pp.f_base = fa; pp.pair_n = (fa + 1 < p->S) ? 2 : 1;
+            rc = ssim ? launch_sweep<false, true>(pp, st) : launch_sweep<false, false>(pp, st);
+        }
+        if (rc == PML_OK)
+            PML_LAUNCH(select_kernel, dim3(pp.n_chunks * pp.n_strips, pp.B, pp.n_pass), dim3(32), 0, st, pp);
+        pp.mode = 2;
+        for (int fa = 0; grad && fa < p->S && rc == PML_OK; fa += 2) {
+            pp.f_base = fa; pp.pair_n = (fa + 1 < p->S) ? 2 : 1;
+            rc = ssim ? launch_sweep<true, true>(pp, st) : launch_sweep<true, false>(pp, st);
+        }
+    } else if (pl.sweep) {
         if (grad) rc = ssim ? launch_sweep<true, true>(pp, st) : launch_sweep<true, false>(pp, st);
         else      rc = ssim ? launch_sweep<false, true>(pp, st) : launch_sweep<false, false>(pp, st);
     } else if (grad) rc = ssim ? dispatch_S<true, true>(p->S, pp, pl.n_cta, pl.NT, low_cells, st)

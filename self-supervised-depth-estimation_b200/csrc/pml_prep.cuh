@@ -44,8 +44,11 @@ struct IdentityParams {
     const float* target;
     const float* src0;
     const float* src1;     // == src0 when S == 1
-    float* out;            // [B, n_out, H, W], n_out = avg ? 1 : S
-    int B, H, W, S, avg;
+    float* out;            // [B, n_out, H, W], n_out = avg ? 1 : total source frames
+    int B, H, W, S, avg;   // S: frames of THIS launch (1 or 2); more frames are swept pair by pair
+    int n_out, plane_off;  // output planes per image, first plane written by this launch
+    int accumulate;        // avg: add to what an earlier pair wrote
+    float inv_total;       // avg: 1 / total source frames
     int TH, n_strips, n_chunks;
 };
 
@@ -62,8 +65,7 @@ identity_sweep_kernel(const IdentityParams p) {
     const int rx = reflect1(clampi(cx, -1, W), W);
     const bool owned = (cx >= x0) && (cx < x1);
     const int b3p = b * 3 * plane;
-    const int n_out = p.avg ? 1 : p.S;
-    float* out_b = p.out + (size_t)b * n_out * plane;
+    float* out_b = p.out + ((size_t)b * p.n_out + p.plane_off) * plane;
 
     float hy1[3], hy2[3], hyy1[3], hyy2[3];
     float2 hx1[3], hx2[3], hxx1[3], hxx2[3], hxy1[3], hxy2[3];
@@ -121,7 +123,8 @@ identity_sweep_kernel(const IdentityParams p) {
             else rp = f2(l1_prev.x * (1.0f / 3.0f), l1_prev.y * (1.0f / 3.0f));
             const int pix = py * W + cx;
             if (p.avg) {
-                out_b[pix] = (p.S > 1) ? (rp.x + rp.y) / 2.0f : rp.x;   // trainer.py:565-566
+                const float v = ((p.S > 1) ? rp.x + rp.y : rp.x) * p.inv_total;   // trainer.py:565-566
+                out_b[pix] = p.accumulate ? out_b[pix] + v : v;
             } else {
                 out_b[pix] = rp.x;
                 if (p.S > 1) out_b[plane + pix] = rp.y;

@@ -162,8 +162,12 @@ sweep_kernel(const PhotoParams p) {
 
     const bool automask = !(p.flags & PML_FLAG_NO_AUTOMASK);
     const bool avg = (p.flags & PML_FLAG_AVG_REPROJ) != 0;
-    const int n_id = automask ? (avg ? 1 : S) : 0;
-    const int f1 = (S > 1) ? 1 : 0;                       // frame in the second half of every pair
+    const int mode = p.mode;                              // see PhotoParams::mode
+    const int n_sel = automask ? (avg ? 1 : S) : 0;       // identity candidates of the selection
+    const int n_id = (mode == 0) ? n_sel : 0;             // ... evaluated by this launch
+    const int fa = p.f_base;                              // frames in the two halves of every pair
+    const bool two = p.pair_n > 1;
+    const int fb = two ? fa + 1 : fa;                     // one frame: it is aliased into the second half
 
     // ---- per-warp shared memory ----------------------------------------------------------------
     float* wsm = smem;
@@ -175,7 +179,7 @@ sweep_kernel(const PhotoParams p) {
     float rc0, rc1, rc2;    // column part of the back-projection ray r = inv_K[:3,:3] @ (x, y, 1)
     {
         if (lane < 24) {
-            const int e = lane >> 1, f = (lane & 1) ? f1 : 0, i = e >> 2, j = e & 3;
+            const int e = lane >> 1, f = (lane & 1) ? fb : fa, i = e >> 2, j = e & 3;
             const float* Kb = p.K + b * 16;
             const float* Tb = p.T[f] + b * 16;
             float a = 0.f;
@@ -209,8 +213,8 @@ sweep_kernel(const PhotoParams p) {
     // All global addressing is `parameter pointer [32-bit element index]`: every tensor of a call has
     // fewer than 2^31 elements (checked on the host).
     const float* __restrict__ tgt_g = p.target;
-    const float* __restrict__ src0_g = p.src[0];
-    const float* __restrict__ src1_g = p.src[f1];
+    const float* __restrict__ src0_g = p.src[fa];
+    const float* __restrict__ src1_g = p.src[fb];
     const float* __restrict__ disp_g = ps.disp;
     const float* __restrict__ id_g = p.identity;
     const float* __restrict__ nz_g = ps.noise;
@@ -221,7 +225,7 @@ sweep_kernel(const PhotoParams p) {
     const float wscale = (float)W / (float)(W - 1), hscale = (float)H / (float)(H - 1);
     const float wmax = (float)(W - 1), hmax = (float)(H - 1);
     const float wmax1 = (float)(W - 2), hmax1 = (float)(H - 2);
-    const bool emit_any = (ps.depth != nullptr) || (ps.warped != nullptr);
+    const bool emit_any = (mode != 2) && ((ps.depth != nullptr && fa == 0) || (ps.warped != nullptr));
 
     // ---- rolling state ---------------------------------------------------------------------------
     float hy1[3], hy2[3], hyy1[3], hyy2[3];
@@ -465,12 +469,12 @@ sweep_kernel(const PhotoParams p) {
         }
         if (emit_any && col_owned && (r >= y0) && (r < y1)) {   // trainer.py:480, :508 (on request)
             const int o = r * W + cx;
-            if (ps.depth != nullptr) ps.depth[bp + o] = D;
+            if (ps.depth != nullptr && fa == 0) ps.depth[bp + o] = D;
             if (ps.warped != nullptr) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    ps.warped[b3p + c * plane + o] = xv[c].x;
-                    if (S > 1) ps.warped[(size_t)p.B * 3 * plane + b3p + c * plane + o] = xv[c].y;
+                    ps.warped[(size_t)fa * p.B * 3 * plane + b3p + c * plane + o] = xv[c].x;
+                    if (two) ps.warped[(size_t)fb * p.B * 3 * plane + b3p + c * plane + o] = xv[c].y;
                 }
             }
         }
@@ -522,7 +526,21 @@ sweep_kernel(const PhotoParams p) {
         l1_prev = l1_cur;
 
         float2 wgt = splat(0.f);
-        if (p_valid) {
+        if (mode == 1) {
+            // more than two source frames, first sweep: only the reprojection losses of this pair
+            if (p_valid && col_owned && py >= y0 && py < y1) {
+                float* rq = p.rp + ((size_t)(pass_i * S + fa) * p.B + b) * plane + (py * W + cx);
+                rq[0] = rp.x;
+                if (two) rq[(size_t)p.B * plane] = rp.y;
+            }
+        } else if (mode == 2) {
+            // ... second sweep: the selection was made by select_kernel over all frames
+            if (p_valid) {
+                const int idx = ps.argmin[bp + py * W + cx];
+                if (avg) wgt = (idx == n_sel) ? f2(1.0f / (float)S, two ? 1.0f / (float)S : 0.f) : splat(0.f);
+                else wgt = f2(idx == n_sel + fa ? 1.f : 0.f, (two && idx == n_sel + fb) ? 1.f : 0.f);
+            }
+        } else if (p_valid) {
             // candidates in the reference's order: identity (+noise) first, then reprojection
             // (trainer.py:597); torch.min returns the first minimum.
             float best = 3.0e38f;
@@ -539,12 +557,12 @@ sweep_kernel(const PhotoParams p) {
                 }
             }
             if (avg) {
-                const float m = (S > 1) ? (rp.x + rp.y) / 2.0f : rp.x;
+                const float m = two ? (rp.x + rp.y) / 2.0f : rp.x;
                 if (m < best) { best = m; best_i = n_id; }
-                if (best_i == n_id) wgt = (S > 1) ? splat(0.5f) : f2(1.f, 0.f);
+                if (best_i == n_id) wgt = two ? splat(0.5f) : f2(1.f, 0.f);
             } else {
                 if (rp.x < best) { best = rp.x; best_i = n_id; }
-                if (S > 1 && rp.y < best) { best = rp.y; best_i = n_id + 1; }
+                if (two && rp.y < best) { best = rp.y; best_i = n_id + 1; }
                 wgt = f2(best_i == n_id ? 1.f : 0.f, best_i == n_id + 1 ? 1.f : 0.f);
             }
             if (col_owned && py >= y0 && py < y1) {
@@ -586,18 +604,80 @@ sweep_kernel(const PhotoParams p) {
     float* out = p.part + (size_t)item * p.part_stride;
     {
         const float v = warp_sum(loss_acc);
-        if (lane == 0) out[0] = v;
+        if (lane == 0 && mode == 0) out[0] = v;
     }
     if (GRAD) {
 #pragma unroll
         for (int e = 0; e < 12; ++e) {
             const float a = warp_sum(gP[e].x), c = warp_sum(gP[e].y);
             if (lane == 0) {
-                out[1 + e] = a;
-                if (S > 1) out[1 + 12 + e] = c;
+                out[1 + 12 * fa + e] = a;
+                if (two) out[1 + 12 * fb + e] = c;
             }
         }
     }
+}
+
+// More than two source frames: per-pixel minimum over the identity candidates (+ tie-break noise)
+// and the reprojection losses of ALL frames (trainer.py:592-610), between the two sweeps.  Same work
+// items as the sweep (one warp per strip item) so that the loss partial lands in the item's row.
+__global__ void __launch_bounds__(32)
+select_kernel(const PhotoParams p) {
+    const int lane = threadIdx.x, b = blockIdx.y, pass_i = blockIdx.z;
+    const int chunk = blockIdx.x / p.n_strips, strip = blockIdx.x - chunk * p.n_strips;
+    const int item = (pass_i * p.B + b) * (p.n_chunks * p.n_strips) + blockIdx.x;
+    const PassDev& ps = p.pass[pass_i];
+    const int H = p.H, W = p.W, S = p.S, plane = H * W;
+    const int x0 = strip * kSweepTW, x1 = min(x0 + kSweepTW, W);
+    const int y0 = chunk * p.TH, y1 = min(y0 + p.TH, H);
+    const int cx = x0 + lane;
+    const bool automask = !(p.flags & PML_FLAG_NO_AUTOMASK);
+    const bool avg = (p.flags & PML_FLAG_AVG_REPROJ) != 0;
+    const int n_id = automask ? (avg ? 1 : S) : 0;
+    const float* id_b = p.identity + (size_t)b * n_id * plane;
+    const float* nz_b = (ps.noise != nullptr) ? ps.noise + (size_t)b * n_id * plane : nullptr;
+    const float* rp_b = p.rp + ((size_t)pass_i * S * p.B + b) * plane;     // frame stride: B * plane
+    const uint32_t key = (uint32_t)p.seed ^ ((uint32_t)(p.seed >> 32) * 0x9E3779B9u);
+    float loss_acc = 0.f;
+    if (lane < kSweepTW && cx < x1) {
+        for (int y = y0; y < y1; ++y) {
+            const int pix = y * W + cx;
+            float best = 3.0e38f;
+            int best_i = 0;
+            if (n_id > 0) {
+                float nz[4] = {0.f, 0.f, 0.f, 0.f};
+                if (nz_b == nullptr) {
+                    philox2_normal2(key, (uint32_t)(b * plane + pix), (uint32_t)pass_i, nz[0], nz[1]);
+                    if (n_id > 2) philox2_normal2(key, (uint32_t)(b * plane + pix), (uint32_t)pass_i + 0x10000u, nz[2], nz[3]);
+                }
+#pragma unroll
+                for (int i = 0; i < PML_MAX_SOURCES; ++i) {
+                    if (i < n_id) {
+                        const float nv = (nz_b != nullptr) ? __ldg(nz_b + (size_t)i * plane + pix) : nz[i];
+                        const float cand = fmaf(nv, kTieNoise, __ldg(id_b + (size_t)i * plane + pix));
+                        if (cand < best) { best = cand; best_i = i; }
+                    }
+                }
+            }
+            float rsum = 0.f;
+#pragma unroll
+            for (int f = 0; f < PML_MAX_SOURCES; ++f) {
+                if (f < S) {
+                    const float r = __ldg(rp_b + (size_t)f * p.B * plane + pix);
+                    if (avg) rsum += r;
+                    else if (r < best) { best = r; best_i = n_id + f; }
+                }
+            }
+            if (avg) {
+                const float m = rsum / (float)S;      // trainer.py:585-586
+                if (m < best) { best = m; best_i = n_id; }
+            }
+            loss_acc += best;
+            ps.argmin[(size_t)b * plane + pix] = (uint8_t)best_i;
+        }
+    }
+    const float v = warp_sum(loss_acc);
+    if (lane == 0) p.part[(size_t)item * p.part_stride] = v;
 }
 
 inline size_t sweep_smem_bytes() { return (size_t)kSweepWarps * kSweepWarpFloats * sizeof(float) + 16; }

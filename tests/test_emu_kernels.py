@@ -44,6 +44,19 @@ def test_three_sources_with_stereo(emu_lib):
     parity.check(got, opt, "trainer", inputs, outputs, 9, sources=(-1, 1, "s"))
 
 
+@pytest.mark.parametrize("sources,over", [((-1, 1, -2, 2), {}), ((-1, 1, "s"), dict(avg_reprojection=True)),
+                                          ((-1, 1, -2), dict(disable_automasking=True)), ((-1, 1, -2, 2), dict(no_ssim=True))])
+def test_more_than_two_sources_pair_sweeps(emu_lib, sources, over, monkeypatch):
+    # S > 2: forward sweep per frame pair -> select_kernel -> forward+adjoint sweep per pair
+    # (three frames default to the CTA-strip kernel; force the pair sweeps here)
+    monkeypatch.setenv("PML_KERNEL", "sweep")
+    B, H, W = 1, 32, 64
+    opt = synthetic.make_options(H, W, batch_size=B, **over)
+    inputs, outputs = synthetic.make_batch(B, H, W, sources=sources, seed=6)
+    got = common.run_product(opt, inputs, outputs, "trainer", device="cpu", noise_seed=4, sources=sources)
+    parity.check(got, opt, "trainer", inputs, outputs, 4, sources=sources)
+
+
 def test_philox_noise_path_runs_and_is_deterministic(emu_lib):
     variant, opt, inputs, outputs, r32, r64, seed = common.load_golden("trainer_static")
     torch.manual_seed(1)

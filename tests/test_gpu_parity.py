@@ -48,6 +48,19 @@ def test_against_oracle(cuda_lib, name):
     print(name, rep)
 
 
+@pytest.mark.parametrize("kernel", ["cta", "sweep", "pipe"])
+def test_kernel_generations_agree(cuda_lib, kernel, monkeypatch):
+    """The CTA-strip kernel, the warp-strip sweep (pair sweeps for S > 2) and the experimental
+    three-stage pipeline are interchangeable: each passes the same parity check."""
+    monkeypatch.setenv("PML_KERNEL", kernel)
+    for sources in ((-1, 1), (-1, 1, "s")):
+        B, H, W = 2, 96, 320
+        opt = synthetic.make_options(H, W, batch_size=B)
+        inputs, outputs = synthetic.make_batch(B, H, W, sources=sources, seed=41)
+        got = common.run_product(opt, inputs, outputs, "trainer", device="cuda", noise_seed=6, sources=sources)
+        parity.check(got, opt, "trainer", inputs, outputs, 6, sources=sources)
+
+
 def _full_size(B=12, H=192, W=640, seed=0):
     opt = synthetic.make_options(H, W, batch_size=B)
     inputs, outputs = synthetic.make_batch(B, H, W, seed=seed)
