@@ -46,6 +46,8 @@ int validate(const pml_problem* p, bool grad) {
     if (!p) return PML_ERR_INVALID;
     if (p->B < 1 || p->H < 4 || p->W < 4 || p->n_pass < 1) return PML_ERR_INVALID;
     if (p->S < 1 || p->S > PML_MAX_SOURCES || p->n_pass > PML_MAX_PASSES) return PML_ERR_UNSUPPORTED;
+    // the kernels index every tensor with 32-bit element offsets; the largest is [B, max(3, S), H, W]
+    if ((long long)p->B * (p->S > 3 ? p->S : 3) * p->H * p->W >= (1LL << 31)) return PML_ERR_UNSUPPORTED;
     if (!p->target || !p->K || !p->inv_K || !p->losses) return PML_ERR_INVALID;
     if (grad && (!p->grad_T || !p->grad_disp_const)) return PML_ERR_INVALID;
     for (int f = 0; f < p->S; ++f)
