@@ -170,7 +170,8 @@ int launch_sweep(const PhotoParams& pp, cudaStream_t st) {
     if (pp.B > 65535) return PML_ERR_UNSUPPORTED;
     const dim3 grid(pp.n_chunks * pp.n_strips, pp.B, pp.n_pass);
     // PML_KERNEL=pipe: three-stage warp-specialised pipeline (pml_pipe.cuh) instead of the single-warp sweep
-    static const bool pipe = [] { const char* k = getenv("PML_KERNEL"); return k && k[0] == 'p'; }();
+    const char* kenv = getenv("PML_KERNEL");
+    const bool pipe = kenv && kenv[0] == 'p';
     if (pipe && pp.mode == 0 && pp.S <= 2) PML_LAUNCH((pipe_kernel<GRAD, SSIM>), grid, dim3(96), pipe_smem_bytes(), st, pp);
     else      PML_LAUNCH((sweep_kernel<GRAD, SSIM>), grid, dim3(kSweepWarps * 32), smem, st, pp);
     return PML_OK;

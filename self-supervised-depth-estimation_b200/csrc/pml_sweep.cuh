@@ -525,6 +525,18 @@ sweep_kernel(const PhotoParams p) {
         }
         l1_prev = l1_cur;
 
+        // In-kernel tie-break noise (no noise tensor given).  Box-Muller on 32-bit uniforms is bounded,
+        // |n| <= sqrt(-2 ln 2^-32) = 6.66, so noise * 1e-5 cannot change the selection where the
+        // candidates are further apart than 1.4e-4; the generator only runs for row steps in which
+        // some pixel of the strip is that close (always on static frames, whose identity losses are 0).
+        if (mode == 0 && n_id > 0 && nz_g == nullptr) {
+            const float m_id = (n_id > 1) ? fminf(idv0, idv1) : idv0;
+            const float m_rp = avg ? (two ? (rp.x + rp.y) * 0.5f : rp.x) : (two ? fminf(rp.x, rp.y) : rp.x);
+            const bool close = (n_id > 1 && fabsf(idv0 - idv1) < 1.4e-4f) || (fabsf(m_id - m_rp) < 1.4e-4f);
+            if (__any_sync(0xffffffffu, close && p_valid))
+                philox2_normal2((uint32_t)p.seed ^ ((uint32_t)(p.seed >> 32) * 0x9E3779B9u),
+                                (uint32_t)(bp + py * W + cx), (uint32_t)pass_i, nzv0, nzv1);
+        }
         float2 wgt = splat(0.f);
         if (mode == 1) {
             // more than two source frames, first sweep: only the reprojection losses of this pair
@@ -547,9 +559,6 @@ sweep_kernel(const PhotoParams p) {
             int best_i = 0;
             const int pix = py * W + cx;
             if (n_id > 0) {
-                if (nz_g == nullptr)
-                    philox2_normal2((uint32_t)p.seed ^ ((uint32_t)(p.seed >> 32) * 0x9E3779B9u),
-                                    (uint32_t)(bp + pix), (uint32_t)pass_i, nzv0, nzv1);
                 best = fmaf(nzv0, kTieNoise, idv0);
                 if (n_id > 1) {
                     const float cand = fmaf(nzv1, kTieNoise, idv1);

@@ -187,6 +187,11 @@ template <class T> static inline T __shfl_up_sync(unsigned, T v, int d) {
     return r;
 }
 template <class T> static inline T __shfl_sync(unsigned, T v, int l) { return emu_shfl(v, (unsigned)l); }
+static inline int __any_sync(unsigned, int pred) {
+    int r = pred ? 1 : 0;
+    for (int m = 16; m > 0; m >>= 1) r |= __shfl_xor_sync(0xffffffffu, r, m);
+    return r;
+}
 
 static inline float atomicAdd(float* p, float v) { return std::atomic_ref<float>(*p).fetch_add(v); }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return std::atomic_ref<unsigned>(*p).fetch_add(v); }

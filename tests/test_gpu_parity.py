@@ -28,6 +28,12 @@ CONFIGS = {
     "uniform_stress": dict(B=2, H=96, W=320, sources=(-1, 1), variant="trainer", style="uniform"),
     "out_of_frustum": dict(B=2, H=96, W=320, sources=(-1, 1), variant="trainer", style="oof"),
     "tanh_range_disp": dict(B=2, H=64, W=160, sources=(-1, 1), variant="fusion", style="kitti", neg_disp=True),
+    # sizes that are not multiples of the 28-column strips / of the row chunks, odd low-res extents
+    "odd_sizes": dict(B=3, H=72, W=200, sources=(-1, 1), variant="trainer", style="kitti", scales=[0, 1, 2, 3]),
+    "tiny": dict(B=1, H=16, W=32, sources=(-1, 1), variant="trainer", style="uniform", scales=[0, 1]),
+    "single_scale3": dict(B=2, H=64, W=96, sources=(1,), variant="trainer", style="kitti", scales=[3]),
+    "four_sources_avg": dict(B=1, H=64, W=160, sources=(-1, 1, -2, 2), variant="trainer", style="kitti",
+                             opt=dict(avg_reprojection=True)),
 }
 
 
@@ -35,9 +41,12 @@ CONFIGS = {
 def test_against_oracle(cuda_lib, name):
     c = dict(CONFIGS[name])
     B, H, W, sources, variant = c["B"], c["H"], c["W"], c["sources"], c["variant"]
-    opt = synthetic.make_options(H, W, batch_size=B, len_sequence=c.get("len_sequence", 1))
+    kw = dict(c.get("opt", {}))
+    if "scales" in c:
+        kw["scales"] = c["scales"]
+    opt = synthetic.make_options(H, W, batch_size=B, len_sequence=c.get("len_sequence", 1), **kw)
     inputs, outputs = synthetic.make_batch(B, H, W, sources=sources, seed=31, style=c["style"],
-                                           full_res_disp=(variant == "fusion"))
+                                           full_res_disp=(variant == "fusion"), scales=opt.scales)
     if c.get("neg_disp"):
         # Fusion's UpscalePS ends in tanh (fusion_v2.py:234-235): disparities are not confined to
         # [0,1]; keep sigma > 0 so that depth stays finite in the oracle too
