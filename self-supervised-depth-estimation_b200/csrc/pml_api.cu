@@ -4,7 +4,6 @@
 #include "pml_photometric.cuh"
 #include "pml_sweep.cuh"
 #include "pml_prep.cuh"
-#include "pml_pipe.cuh"
 #include "pml_smooth.cuh"
 #include "pml_layers.cuh"
 #include "pml_metrics.cuh"
@@ -71,7 +70,7 @@ int validate(const pml_problem* p, bool grad) {
 bool use_sweep(const pml_problem* p) {
     const char* k = getenv("PML_KERNEL");
     if (k && k[0] == 'c') return false;
-    if (k && (k[0] == 's' || k[0] == 'p')) return true;
+    if (k && k[0] == 's') return true;
     return p->S != 3;
 }
 
@@ -169,11 +168,7 @@ int launch_sweep(const PhotoParams& pp, cudaStream_t st) {
     const size_t smem = sweep_smem_bytes();   // < 48 KB: no opt-in needed
     if (pp.B > 65535) return PML_ERR_UNSUPPORTED;
     const dim3 grid(pp.n_chunks * pp.n_strips, pp.B, pp.n_pass);
-    // PML_KERNEL=pipe: three-stage warp-specialised pipeline (pml_pipe.cuh) instead of the single-warp sweep
-    const char* kenv = getenv("PML_KERNEL");
-    const bool pipe = kenv && kenv[0] == 'p';
-    if (pipe && pp.mode == 0 && pp.S <= 2) PML_LAUNCH((pipe_kernel<GRAD, SSIM>), grid, dim3(96), pipe_smem_bytes(), st, pp);
-    else      PML_LAUNCH((sweep_kernel<GRAD, SSIM>), grid, dim3(kSweepWarps * 32), smem, st, pp);
+    PML_LAUNCH((sweep_kernel<GRAD, SSIM>), grid, dim3(kSweepWarps * 32), smem, st, pp);
     return PML_OK;
 }
 
