@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PML_ABI_VERSION 1
+#define PML_ABI_VERSION 2
 #define PML_MAX_SOURCES 4 /* source frames per target, e.g. (-1, 1, "s") = 3 */
 #define PML_MAX_PASSES 8  /* scales handled by one call */
 
@@ -63,6 +63,11 @@ typedef struct pml_pass {
     float* grad_disp;          /* [B,1,hd,wd] out: d loss_s / d disp_s WITHOUT the per-image mean term
                                   of the smoothness normalisation (that constant is grad_disp_const);
                                   forward_backward only */
+    const float* frame_weight; /* [B,S,H,W] or NULL: --predictive_mask (trainer.py:571-579), the mask
+                                  already resized to H x W; multiplies the reprojection loss of each
+                                  source frame before the mean / min.  Requires PML_FLAG_NO_AUTOMASK
+                                  (the reference's `elif`), set on every pass or on none */
+    float* grad_frame_weight;  /* [B,S,H,W] out: d loss_s / d frame_weight (forward_backward only) */
 } pml_pass;
 
 /* A group of passes that share images, intrinsics and poses (all scales when
@@ -133,6 +138,16 @@ size_t pml_smooth_workspace_bytes(int32_t B, int32_t H, int32_t W);
 /* transformation_from_parameters, layers.py:28-103: axisangle,translation [B,3] -> T [B,4,4] */
 int pml_pose_fwd(const float* axisangle, const float* translation, float* T, int32_t B, int32_t invert, pml_stream_t);
 int pml_pose_bwd(const float* axisangle, const float* translation, const float* g_T, float* g_axisangle, float* g_translation, int32_t B, int32_t invert, pml_stream_t);
+/* F.interpolate(x, [H, W], mode="bilinear", align_corners=False) (trainer.py:474-475 on the
+ * disparities, :574-576 on the predictive mask): x [planes,h,w] -> out [planes,H,W]; bwd is the
+ * transposed resize as a deterministic gather */
+int pml_upsample_fwd(const float* x, float* out, int32_t planes, int32_t h, int32_t w, int32_t H, int32_t W, pml_stream_t);
+int pml_upsample_bwd(const float* g_out, float* g_x, int32_t planes, int32_t h, int32_t w, int32_t H, int32_t W, pml_stream_t);
+/* nn.BCELoss()(mask, ones) (trainer.py:582): out[0] = mean(-max(log(mask), -100)); bwd follows ATen's
+ * binary_cross_entropy_backward, g * (x - 1) / max((1 - x) x, 1e-12) / n */
+size_t pml_bce_workspace_bytes(void);
+int pml_bce_ones_fwd(const float* mask, int64_t n, float* out, void* workspace, size_t workspace_bytes, pml_stream_t);
+int pml_bce_ones_bwd(const float* mask, const float* g_out, float* g_mask, int64_t n, pml_stream_t);
 
 
 /* ---- monitoring metrics: Trainer.compute_depth_losses (trainer.py:624-652) over

@@ -205,7 +205,6 @@ def compute_losses(opt, inputs, outputs, sources=(-1, 1), variant="trainer",
     Returns ``losses`` like the reference plus, under ``outputs``: ``identity_selection/{s}``,
     ``("argmin", s)`` (int64 [B,H,W], what the reference's ``torch.min`` returns) and, with
     keep_maps, ``("margin", s)`` (second-best minus best candidate) and ``("to_optimise", s)``."""
-    assert not opt.predictive_mask, "predictive_mask is a 'next' row (SURVEY.md §8 f4)"
     n_seq = opt.len_sequence if variant == "gru" else 0
     losses = {}
     total = 0
@@ -217,6 +216,15 @@ def compute_losses(opt, inputs, outputs, sources=(-1, 1), variant="trainer",
 
         reproj = torch.cat([reprojection_loss(outputs[("color", f, scale)], target, opt.no_ssim)
                             for f in sources], 1)
+        extra = 0
+        if opt.disable_automasking and getattr(opt, "predictive_mask", False):
+            # trainer.py:571-583: predicted per-frame mask, resized unless v1_multiscale, weights
+            # the reprojection losses; 0.2 * BCE(mask, ones) pushes it towards 1
+            mask = outputs["predictive_mask"][("disp", scale)]
+            if not opt.v1_multiscale:
+                mask = F.interpolate(mask, [opt.height, opt.width], mode="bilinear", align_corners=False)
+            reproj = reproj * mask
+            extra = 0.2 * F.binary_cross_entropy(mask, torch.ones_like(mask))
         if opt.avg_reprojection:
             reproj = reproj.mean(1, keepdim=True)
 
@@ -251,12 +259,22 @@ def compute_losses(opt, inputs, outputs, sources=(-1, 1), variant="trainer",
             else:
                 outputs[("margin", scale)] = torch.full_like(to_opt.detach().reshape(idxs.shape), float("inf"))
 
-        loss = to_opt.mean()
+        loss = extra + to_opt.mean()
         loss = loss + opt.disparity_smoothness * normalised_smooth_loss(disp, color) / (2 ** scale)
         total = total + loss
         losses["loss/{}".format(scale)] = loss
     losses["loss"] = total / len(opt.scales)
     return losses
+
+
+def nest_predictive_mask(outputs):
+    """Test dictionaries keep the predicted masks flat as ``("predictive_mask", s)`` (so they can be
+    stored like every other tensor); the trainers read ``outputs["predictive_mask"][("disp", s)]``
+    (trainer.py:573, written at trainer.py:294)."""
+    flat = [k for k in outputs if isinstance(k, tuple) and k[0] == "predictive_mask"]
+    if flat:
+        outputs["predictive_mask"] = {("disp", k[1]): outputs.pop(k) for k in flat}
+    return outputs
 
 
 def run(opt, inputs, outputs, sources=(-1, 1), variant="trainer", noise=None, dtype=None,
@@ -272,12 +290,15 @@ def run(opt, inputs, outputs, sources=(-1, 1), variant="trainer", noise=None, dt
         return t.clone()
 
     inp = {k: conv(v) for k, v in inputs.items()}
-    out = {k: conv(v) for k, v in outputs.items()}
+    out = nest_predictive_mask({k: conv(v) for k, v in outputs.items()})
     leaves = {}
     if want_grad:
         for s in opt.scales:
             out[("disp", s)].requires_grad_(True)
             leaves["grad_disp/{}".format(s)] = out[("disp", s)]
+            if "predictive_mask" in out:
+                out["predictive_mask"][("disp", s)].requires_grad_(True)
+                leaves["grad_mask/{}".format(s)] = out["predictive_mask"][("disp", s)]
         for f in sources:
             if f != "s":
                 out[("cam_T_cam", 0, f)].requires_grad_(True)

@@ -100,6 +100,9 @@ def run(opt, inputs, outputs, variant="trainer", noise_seed=0, dtype=torch.float
 
     inp = {k: conv(v) for k, v in inputs.items()}
     out = {k: conv(v) for k, v in outputs.items()}
+    flat = [k for k in out if isinstance(k, tuple) and k[0] == "predictive_mask"]
+    if flat:   # trainer.py:573 reads outputs["predictive_mask"]["disp", scale]
+        out["predictive_mask"] = {("disp", k[1]): out.pop(k) for k in flat}
     n_flat = out[("disp", opt.scales[0])].shape[0]
 
     ns = SimpleNamespace(opt=opt, device=torch.device("cpu"), num_scales=len(opt.scales))
@@ -116,14 +119,26 @@ def run(opt, inputs, outputs, variant="trainer", noise_seed=0, dtype=torch.float
         for s in opt.scales:
             out[("disp", s)].requires_grad_(True)
             leaves["grad_disp/{}".format(s)] = out[("disp", s)]
+            if "predictive_mask" in out:
+                out["predictive_mask"][("disp", s)].requires_grad_(True)
+                leaves["grad_mask/{}".format(s)] = out["predictive_mask"][("disp", s)]
         for f in (-1, 1):
             out[("cam_T_cam", 0, f)].requires_grad_(True)
             leaves["grad_T/{}".format(f)] = out[("cam_T_cam", 0, f)]
 
     torch.manual_seed(noise_seed)
-    with _RecordMin() as rec:
-        Trainer.generate_images_pred(ns, inp, out)
-        losses = Trainer.compute_losses(ns, inp, out)
+    # trainer.py:582 builds its BCE target with torch.ones(...) in the DEFAULT dtype, so the float64
+    # run of the predictive-mask branch needs the default switched (that branch draws no noise, so
+    # the generator stream of the other cases is not affected)
+    old_default = torch.get_default_dtype()
+    if "predictive_mask" in out:
+        torch.set_default_dtype(dtype)
+    try:
+        with _RecordMin() as rec:
+            Trainer.generate_images_pred(ns, inp, out)
+            losses = Trainer.compute_losses(ns, inp, out)
+    finally:
+        torch.set_default_dtype(old_default)
     res = {"loss": losses["loss"].detach()}
     for i, s in enumerate(opt.scales):
         res["loss/{}".format(s)] = losses["loss/{}".format(s)].detach()

@@ -8,7 +8,7 @@ import os
 from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t,
                     c_uint32, c_uint64, c_void_p)
 
-PML_ABI_VERSION = 1
+PML_ABI_VERSION = 2
 PML_MAX_SOURCES = 4
 PML_MAX_PASSES = 8
 PML_FLAG_NO_SSIM = 1
@@ -22,7 +22,8 @@ DEFAULT_LIB = os.path.join(_HERE, "libpml.so")
 class PmlPass(Structure):
     _fields_ = [("hd", c_int32), ("wd", c_int32), ("smooth_weight", c_float), ("reserved", c_int32),
                 ("disp", c_void_p), ("smooth_color", c_void_p), ("noise", c_void_p),
-                ("argmin", c_void_p), ("depth", c_void_p), ("warped", c_void_p), ("grad_disp", c_void_p)]
+                ("argmin", c_void_p), ("depth", c_void_p), ("warped", c_void_p), ("grad_disp", c_void_p),
+                ("frame_weight", c_void_p), ("grad_frame_weight", c_void_p)]
 
 
 class PmlProblem(Structure):
@@ -63,6 +64,11 @@ _SIGNATURES = {
     "pml_smooth_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
     "pml_pose_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
     "pml_pose_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
+    "pml_upsample_fwd": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "pml_upsample_bwd": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "pml_bce_workspace_bytes": (c_size_t, []),
+    "pml_bce_ones_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "pml_bce_ones_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "pml_depth_metrics_workspace_bytes": (c_size_t, []),
     "pml_depth_metrics_prepare": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int32] * 9 +
                                   [c_float, c_float, c_void_p]),

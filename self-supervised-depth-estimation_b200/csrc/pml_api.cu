@@ -7,6 +7,7 @@
 #include "pml_smooth.cuh"
 #include "pml_layers.cuh"
 #include "pml_metrics.cuh"
+#include "pml_mask.cuh"
 
 #include <stdlib.h>
 #include <atomic>
@@ -20,7 +21,8 @@ constexpr int kNumSM = 148;   // B200
 inline size_t align16(size_t v) { return (v + 15) & ~size_t(15); }
 
 struct Plan {
-    bool sweep;   // warp-strip kernel (pml_sweep.cuh, S <= 2) instead of the CTA-strip kernel
+    bool sweep;   // warp-strip kernel (pml_sweep.cuh) instead of the CTA-strip kernel
+    bool two_sweeps;   // S > 2 or predictive mask: forward sweep per frame pair, selection, adjoint sweep
     int NT, TW, TH, n_strips, n_chunks, cta_per_pass, n_cta, part_stride;
     int n_id;
     int smooth_blocks[PML_MAX_PASSES], smooth_off[PML_MAX_PASSES], smooth_total;
@@ -55,6 +57,8 @@ int validate(const pml_problem* p, bool grad) {
         const pml_pass& ps = p->pass[i];
         if (!ps.disp || !ps.smooth_color || ps.hd < 2 || ps.wd < 2) return PML_ERR_INVALID;
         if (grad && !ps.grad_disp) return PML_ERR_INVALID;
+        if ((ps.frame_weight != nullptr) != (p->pass[0].frame_weight != nullptr)) return PML_ERR_INVALID;
+        if (ps.frame_weight && !(p->flags & PML_FLAG_NO_AUTOMASK)) return PML_ERR_UNSUPPORTED;   // trainer.py:556 / :571
         if (p->H % ps.hd != 0 || p->W % ps.wd != 0) return PML_ERR_UNSUPPORTED;
         int k = p->H / ps.hd;
         if (p->W / ps.wd != k || (k & (k - 1)) != 0 || k > 64) return PML_ERR_UNSUPPORTED;
@@ -68,6 +72,7 @@ int validate(const pml_problem* p, bool grad) {
 // half of the second pair idle -- there the first-generation CTA-strip kernel (templated on S) is
 // still ahead (3.0 vs 3.4 ms at B=8, 320x1024) and is kept.  PML_KERNEL=cta / sweep force a choice.
 bool use_sweep(const pml_problem* p) {
+    if (p->pass[0].frame_weight) return true;   // predictive mask: pair sweeps around select_kernel
     const char* k = getenv("PML_KERNEL");
     if (k && k[0] == 'c') return false;
     if (k && k[0] == 's') return true;
@@ -135,7 +140,8 @@ Plan make_plan(const pml_problem* p, bool grad) {
     pl.off_imagepart = off; off = align16(off + (size_t)p->n_pass * p->B * 4 * sizeof(float));
     pl.off_smooth = off;   off = align16(off + (size_t)pl.smooth_total * 3 * sizeof(float));
     pl.off_rp = pl.off_argmin = off;
-    if (pl.sweep && p->S > 2) {   // pair-by-pair sweep: reprojection losses of all frames + a selection map
+    pl.two_sweeps = pl.sweep && (p->S > 2 || p->pass[0].frame_weight != nullptr);
+    if (pl.two_sweeps) {   // pair-by-pair sweep: reprojection losses of all frames + a selection map
         off = align16(off + (size_t)p->n_pass * p->S * p->B * p->H * p->W * sizeof(float));
         pl.off_argmin = off;
         off = align16(off + (size_t)p->n_pass * p->B * p->H * p->W);
@@ -259,6 +265,7 @@ int run_loss(const pml_problem* p, void* ws, size_t ws_bytes, cudaStream_t st, b
         PassDev& d = pp.pass[i];
         d.disp = ps.disp; d.noise = ps.noise; d.argmin = ps.argmin; d.depth = ps.depth; d.warped = ps.warped;
         d.grad_disp = grad ? ps.grad_disp : nullptr;
+        d.fw = ps.frame_weight; d.gfw = grad ? ps.grad_frame_weight : nullptr;
         d.hd = ps.hd; d.wd = ps.wd; d.k = p->H / ps.hd;
         d.rscale = (float)ps.hd / (float)p->H;
         d.low_cols = pl.TW / d.k + 3; d.low_rows = pl.TH / d.k + 3;
@@ -270,8 +277,8 @@ int run_loss(const pml_problem* p, void* ws, size_t ws_bytes, cudaStream_t st, b
     pp.cta_per_pass = pl.cta_per_pass; pp.part = part; pp.part_stride = pl.part_stride;
     pp.inv_n = (float)(1.0 / ((double)p->B * p->H * p->W));
     if (p->prof_start) pml_event_record(p->prof_start, st);
-    if (pl.sweep && p->S > 2) {
-        // More than two source frames: (1) forward sweep per frame pair -> reprojection losses,
+    if (pl.two_sweeps) {
+        // More than two source frames (or per-frame weights): (1) forward sweep per frame pair -> reprojection losses,
         // (2) selection over all candidates, (3) forward + adjoint sweep per pair with that selection.
         pp.rp = reinterpret_cast<float*>(base + pl.off_rp);
         for (int i = 0; i < p->n_pass; ++i)

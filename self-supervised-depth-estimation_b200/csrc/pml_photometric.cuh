@@ -25,6 +25,8 @@ struct PassDev {
     float* depth;
     float* warped;
     float* grad_disp;
+    const float* fw;   // [B,S,H,W] per-frame weights of the reprojection losses (predictive mask) or null
+    float* gfw;        // [B,S,H,W] out: d loss / d fw (photometric part) or null
     int hd, wd, k;   // k = H / hd (1, 2, 4, 8, ...)
     float rscale;    // hd / H : ATen area_pixel_compute_scale for align_corners=False
     int low_cols, low_rows;  // extent of the per-CTA low-res accumulator (k > 1)

@@ -551,6 +551,10 @@ sweep_kernel(const PhotoParams p) {
                 const int idx = ps.argmin[bp + py * W + cx];
                 if (avg) wgt = (idx == n_sel) ? f2(1.0f / (float)S, two ? 1.0f / (float)S : 0.f) : splat(0.f);
                 else wgt = f2(idx == n_sel + fa ? 1.f : 0.f, (two && idx == n_sel + fb) ? 1.f : 0.f);
+                if (ps.fw != nullptr) {   // predictive mask (trainer.py:579): d (rp * m) / d rp = m
+                    const float* mq = at(ps.fw, (b * S + fa) * plane + py * W + cx);
+                    wgt = mul2(wgt, f2(__ldg(mq), two ? __ldg(at(mq, plane)) : 0.f));
+                }
             }
         } else if (p_valid) {
             // candidates in the reference's order: identity (+noise) first, then reprojection
@@ -646,6 +650,8 @@ select_kernel(const PhotoParams p) {
     const float* id_b = p.identity + (size_t)b * n_id * plane;
     const float* nz_b = (ps.noise != nullptr) ? ps.noise + (size_t)b * n_id * plane : nullptr;
     const float* rp_b = p.rp + ((size_t)pass_i * S * p.B + b) * plane;     // frame stride: B * plane
+    const float* fw_b = (ps.fw != nullptr) ? ps.fw + (size_t)b * S * plane : nullptr;   // predictive mask
+    float* gfw_b = (ps.gfw != nullptr) ? ps.gfw + (size_t)b * S * plane : nullptr;
     const uint32_t key = (uint32_t)p.seed ^ ((uint32_t)(p.seed >> 32) * 0x9E3779B9u);
     float loss_acc = 0.f;
     if (lane < kSweepTW && cx < x1) {
@@ -669,10 +675,14 @@ select_kernel(const PhotoParams p) {
                 }
             }
             float rsum = 0.f;
+            float rraw[PML_MAX_SOURCES];
 #pragma unroll
             for (int f = 0; f < PML_MAX_SOURCES; ++f) {
+                rraw[f] = 0.f;
                 if (f < S) {
-                    const float r = __ldg(rp_b + (size_t)f * p.B * plane + pix);
+                    float r = __ldg(rp_b + (size_t)f * p.B * plane + pix);
+                    rraw[f] = r;
+                    if (fw_b != nullptr) r *= __ldg(fw_b + (size_t)f * plane + pix);   // trainer.py:579
                     if (avg) rsum += r;
                     else if (r < best) { best = r; best_i = n_id + f; }
                 }
@@ -683,6 +693,15 @@ select_kernel(const PhotoParams p) {
             }
             loss_acc += best;
             ps.argmin[(size_t)b * plane + pix] = (uint8_t)best_i;
+            if (gfw_b != nullptr) {   // d mean(to_optimise) / d mask_f = [f selected] * rp_f / N
+#pragma unroll
+                for (int f = 0; f < PML_MAX_SOURCES; ++f) {
+                    if (f < S) {
+                        const float sel = avg ? (best_i == n_id ? 1.0f / (float)S : 0.f) : (best_i == n_id + f ? 1.f : 0.f);
+                        gfw_b[(size_t)f * plane + pix] = sel * rraw[f] * p.inv_n;
+                    }
+                }
+            }
         }
     }
     const float v = warp_sum(loss_acc);

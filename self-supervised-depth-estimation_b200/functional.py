@@ -42,7 +42,8 @@ def _ptr(t: Optional[torch.Tensor]):
 
 class _PhotometricLoss(torch.autograd.Function):
     """inputs: cfg, then tensors laid out as
-    disps[n_pass] | Ts[S] | target | K | inv_K | sources[S] | smooth_colors[n_pass] | noise[n_pass or 0]"""
+    disps[n_pass] | Ts[S] | frame_weights[n_pass or 0] | target | K | inv_K | sources[S] |
+    smooth_colors[n_pass] | noise[n_pass or 0]"""
 
     @staticmethod
     def forward(ctx, cfg: Dict, *tensors):
@@ -52,6 +53,8 @@ class _PhotometricLoss(torch.autograd.Function):
         it = iter(tensors)
         disps = [next(it) for _ in range(n_pass)]
         Ts = [next(it) for _ in range(S)]
+        fws = [next(it) for _ in range(n_pass)] if cfg.get("has_fw") else [None] * n_pass
+        n_diff = n_pass + S + (n_pass if cfg.get("has_fw") else 0)
         target, K, inv_K = next(it), next(it), next(it)
         sources = [next(it) for _ in range(S)]
         colors = [next(it) for _ in range(n_pass)]
@@ -61,11 +64,11 @@ class _PhotometricLoss(torch.autograd.Function):
         if C != 3:
             raise ValueError("target must be [B,3,H,W]")
         need = ctx.needs_input_grad[1:]
-        if any(need[n_pass + S:]):
+        if any(need[n_diff:]):
             raise NotImplementedError(
                 "gradients with respect to images / intrinsics / noise are not produced by libpml "
                 "(the reference never requests them: colour inputs carry no grad, trainer.py:233-237)")
-        want_grad = any(need[:n_pass + S])
+        want_grad = any(need[:n_diff])
         dev = target.device
         f32 = dict(device=dev, dtype=torch.float32)
 
@@ -87,7 +90,7 @@ class _PhotometricLoss(torch.autograd.Function):
             raise ValueError("K / inv_K must be [B,4,4]")
 
         emit_depth, emit_warped = cfg.get("emit_depth", ()), cfg.get("emit_warped", ())
-        argmins, depths, warpeds, gdisps = [], [], [], []
+        argmins, depths, warpeds, gdisps, gfws = [], [], [], [], []
         for i in range(n_pass):
             d = disps[i]
             if d.dim() != 4 or d.shape[0] != B or d.shape[1] != 1:
@@ -116,6 +119,14 @@ class _PhotometricLoss(torch.autograd.Function):
                 g = torch.empty_like(d)
                 ps.grad_disp = g.data_ptr()
                 gdisps.append(g)
+            if fws[i] is not None:
+                if tuple(fws[i].shape) != (B, S, H, W):
+                    raise ValueError("frame weights %d must be [B,%d,H,W] (the predictive mask at full resolution)" % (i, S))
+                ps.frame_weight = fws[i].data_ptr()
+                if want_grad:
+                    gw = torch.empty_like(fws[i])
+                    ps.grad_frame_weight = gw.data_ptr()
+                    gfws.append(gw)
         losses4 = torch.empty((n_pass, 4), **f32)
         prob.losses = losses4.data_ptr()
         if want_grad:
@@ -139,7 +150,7 @@ class _PhotometricLoss(torch.autograd.Function):
         ctx.cfg = cfg
         ctx.set_materialize_grads(False)   # no zero-filled grads for the non-differentiable by-products
         if want_grad:
-            ctx.gdisps, ctx.grad_T, ctx.grad_const = gdisps, grad_T, grad_const
+            ctx.gdisps, ctx.grad_T, ctx.grad_const, ctx.gfws = gdisps, grad_T, grad_const, gfws
             ctx.shapes = [(d.shape[2], d.shape[3]) for d in disps]
             ctx.B, ctx.S, ctx.consumed = B, S, False
         loss = losses4[:, 0].clone()
@@ -173,7 +184,9 @@ class _PhotometricLoss(torch.autograd.Function):
             grads.append(ctx.gdisps[i] if need[i] else None)
         for f in range(S):
             grads.append(gT_out[f] if need[n_pass + f] else None)
-        grads += [None] * (len(need) - n_pass - S)
+        for i, gw in enumerate(ctx.gfws):   # d loss_s / d mask_s, scaled by the incoming gradient
+            grads.append(gw.mul_(up[i]) if need[n_pass + S + i] else None)
+        grads += [None] * (len(need) + 1 - len(grads))
         return tuple(grads)
 
 
@@ -182,13 +195,18 @@ def photometric_loss(target, sources: Sequence[torch.Tensor], K, inv_K, Ts: Sequ
                      smooth_weights: Sequence[float], min_depth=0.1, max_depth=100.0,
                      no_ssim=False, disable_automasking=False, avg_reprojection=False,
                      noise: Optional[Sequence[torch.Tensor]] = None, seed: int = 0,
-                     emit_depth: Sequence[int] = (), emit_warped: Sequence[int] = (), prof_events=None):
+                     emit_depth: Sequence[int] = (), emit_warped: Sequence[int] = (), prof_events=None,
+                     frame_weights: Optional[Sequence[torch.Tensor]] = None):
     """Fused view synthesis + photometric loss for ``len(disps)`` scales sharing one image set.
 
     Returns a dict: ``loss`` [n_pass] (differentiable w.r.t. ``disps`` and ``Ts``; element s is
     the reference's ``losses["loss/s"]``, trainer.py:618), ``terms`` [n_pass,4] (loss, photometric
     mean, smoothness, 0), ``argmin`` list of uint8 [B,H,W] (torch.min index, trainer.py:604),
-    ``depth`` {pass: [B,1,H,W]} and ``warped`` {pass: [S,B,3,H,W]} for the requested passes."""
+    ``depth`` {pass: [B,1,H,W]} and ``warped`` {pass: [S,B,3,H,W]} for the requested passes.
+
+    ``frame_weights`` (one [B,S,H,W] tensor per scale, differentiable) is the ``--predictive_mask``
+    ablation (trainer.py:571-579): the mask, already resized to H x W, multiplies each frame's
+    reprojection loss before the mean / min; like the reference it needs ``disable_automasking``."""
     n_pass, S = len(disps), len(sources)
     if not (1 <= n_pass <= PML_MAX_PASSES):
         raise ValueError("1..%d scales per call" % PML_MAX_PASSES)
@@ -199,10 +217,16 @@ def photometric_loss(target, sources: Sequence[torch.Tensor], K, inv_K, Ts: Sequ
     flags = (PML_FLAG_NO_SSIM if no_ssim else 0) | (PML_FLAG_NO_AUTOMASK if disable_automasking else 0) | \
             (PML_FLAG_AVG_REPROJ if avg_reprojection else 0)
     use_noise = noise is not None and not disable_automasking
+    if frame_weights is not None:
+        if not disable_automasking:
+            raise ValueError("frame_weights (predictive mask) are only used with disable_automasking (trainer.py:556,571)")
+        if len(frame_weights) != n_pass:
+            raise ValueError("one frame-weight tensor per scale")
     cfg = dict(n_pass=n_pass, S=S, flags=flags, min_depth=float(min_depth), max_depth=float(max_depth),
                smooth_weights=[float(w) for w in smooth_weights], has_noise=use_noise, seed=int(seed) & (2 ** 64 - 1),
-               emit_depth=tuple(emit_depth), emit_warped=tuple(emit_warped), prof_events=prof_events)
-    tensors = list(disps) + list(Ts) + [target, K, inv_K] + list(sources) + list(smooth_colors)
+               emit_depth=tuple(emit_depth), emit_warped=tuple(emit_warped), prof_events=prof_events,
+               has_fw=frame_weights is not None)
+    tensors = list(disps) + list(Ts) + (list(frame_weights) if frame_weights is not None else []) + [target, K, inv_K] + list(sources) + list(smooth_colors)
     if use_noise:
         tensors += list(noise)
     outs = _PhotometricLoss.apply(cfg, *tensors)
@@ -383,6 +407,61 @@ class _Pose(torch.autograd.Function):
         lib.check(lib.pml_pose_bwd(_ptr(aa), _ptr(tr), _ptr(gT), _ptr(ga), _ptr(gt), aa.shape[0], 1 if invert else 0,
                                    _stream_ptr(aa)), "pml_pose_bwd")
         return ga.reshape(sa), gt.reshape(st), None
+
+
+class _Upsample(torch.autograd.Function):
+    """F.interpolate(x, [H, W], mode="bilinear", align_corners=False) (trainer.py:474-475, :574-576)."""
+    @staticmethod
+    def forward(ctx, x, H, W):
+        lib = get_library()
+        x = _check(x, "x", lib)
+        if x.dim() != 4:
+            raise ValueError("x must be [B,C,h,w]")
+        B, C, h, w = x.shape
+        out = torch.empty((B, C, H, W), device=x.device, dtype=torch.float32)
+        lib.check(lib.pml_upsample_fwd(_ptr(x), _ptr(out), B * C, h, w, H, W, _stream_ptr(x)), "pml_upsample_fwd")
+        ctx.dims = (B, C, h, w, H, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = get_library()
+        B, C, h, w, H, W = ctx.dims
+        g = g.contiguous()
+        gx = torch.empty((B, C, h, w), device=g.device, dtype=torch.float32)
+        lib.check(lib.pml_upsample_bwd(_ptr(g), _ptr(gx), B * C, h, w, H, W, _stream_ptr(g)), "pml_upsample_bwd")
+        return gx, None, None
+
+
+class _BceOnes(torch.autograd.Function):
+    """nn.BCELoss()(mask, torch.ones_like(mask)) (trainer.py:582) -> 0-dim tensor."""
+    @staticmethod
+    def forward(ctx, mask):
+        lib = get_library()
+        mask = _check(mask, "mask", lib)
+        out = torch.empty((), device=mask.device, dtype=torch.float32)
+        nb = lib.pml_bce_workspace_bytes()
+        ws = torch.empty(nb, device=mask.device, dtype=torch.uint8)
+        lib.check(lib.pml_bce_ones_fwd(_ptr(mask), mask.numel(), _ptr(out), _ptr(ws), nb, _stream_ptr(mask)), "pml_bce_ones_fwd")
+        ctx.save_for_backward(mask)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = get_library()
+        (mask,) = ctx.saved_tensors
+        g = g.contiguous().to(torch.float32)
+        gm = torch.empty_like(mask)
+        lib.check(lib.pml_bce_ones_bwd(_ptr(mask), _ptr(g), _ptr(gm), mask.numel(), _stream_ptr(mask)), "pml_bce_ones_bwd")
+        return gm
+
+
+def upsample_bilinear(x: torch.Tensor, height: int, width: int) -> torch.Tensor:
+    return _Upsample.apply(x, int(height), int(width))
+
+
+def bce_against_ones(mask: torch.Tensor) -> torch.Tensor:
+    return _BceOnes.apply(mask)
 
 
 # ------------------------------------------------------------------------------------------------

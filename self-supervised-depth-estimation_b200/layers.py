@@ -73,3 +73,9 @@ class SSIM(nn.Module):
 def get_smooth_loss(disp, img):
     """layers.py:202-215: edge-aware smoothness of ``disp`` [B,1,H,W] under ``img`` [B,C,H,W]."""
     return _F._SmoothLoss.apply(disp, img)
+
+
+def interpolate_bilinear(x, size):
+    """The reference's ``F.interpolate(x, [H, W], mode="bilinear", align_corners=False)`` calls
+    (trainer.py:474-475 on disparities, :574-576 on the predictive mask): [B,C,h,w] -> [B,C,H,W]."""
+    return _F.upsample_bilinear(x, size[0], size[1])

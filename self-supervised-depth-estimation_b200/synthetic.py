@@ -146,7 +146,7 @@ def _invert_flow(fu, fv, xs, ys, iters=10):
 
 
 def make_batch(batch=12, height=192, width=640, scales=(0, 1, 2, 3), sources=(-1, 1), seed=0,
-               style="kitti", full_res_disp=False, device="cpu", dtype=torch.float32):
+               style="kitti", full_res_disp=False, device="cpu", dtype=torch.float32, predictive_mask=False):
     """Build (inputs, outputs) dictionaries in the reference schema.
 
     style:
@@ -158,6 +158,9 @@ def make_batch(batch=12, height=192, width=640, scales=(0, 1, 2, 3), sources=(-1
       "constant" constant-colour images (SSIM denominators collapse to C1*C2)
       "oof"      poses that throw most samples out of the frustum (border clamp path)
     full_res_disp: every ``("disp", s)`` is emitted at H x W (trainer_fusion.py:427-433).
+    predictive_mask: also emit ``outputs[("predictive_mask", s)]`` [B,S,h_s,w_s], a sigmoid of smooth
+      noise like the mask decoder's output (trainer.py:294, networks/depth_decoder.py:62-66); the
+      trainers read it as ``outputs["predictive_mask"][("disp", s)]`` (trainer.py:573).
     """
     g = torch.Generator().manual_seed(seed)
     num_scales = max(scales) + 1
@@ -238,6 +241,12 @@ def make_batch(batch=12, height=192, width=640, scales=(0, 1, 2, 3), sources=(-1
             img = inputs[("color", f, 0)].clamp(0, 1).contiguous()
             for s in range(num_scales):
                 inputs[("color", f, s)] = (img if s == 0 else F.avg_pool2d(img, 2 ** s)).contiguous()
+
+    if predictive_mask:
+        for s in scales:
+            h, w = height // 2 ** s, width // 2 ** s
+            n = _box_blur(torch.randn(batch, len(sources), h, w, generator=g), 5)
+            outputs[("predictive_mask", s)] = torch.sigmoid(4.0 * n + 1.0).contiguous()
 
     def cvt(t):
         return t.to(device=device, dtype=dtype) if t.is_floating_point() else t.to(device)

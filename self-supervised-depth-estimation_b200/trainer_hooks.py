@@ -54,8 +54,8 @@ def _gather(inputs, key, n_seq, cache):
 
 def _run_fused(self, inputs, outputs):
     opt = self.opt
-    if _opt(opt, "predictive_mask", False):
-        raise NotImplementedError("predictive_mask is not on the fused path yet (SURVEY.md §8 f4)")
+    # trainer.py:571: the predicted mask is only consulted when automasking is off (`elif`)
+    pmask = bool(_opt(opt, "predictive_mask", False)) and bool(opt.disable_automasking)
     variant = _opt(opt, "pml_variant", "trainer")
     sources = list(_opt(opt, "pml_sources", [-1, 1]))
     n_seq = _opt(opt, "len_sequence", 0) if variant == "gru" else 0
@@ -94,9 +94,17 @@ def _run_fused(self, inputs, outputs):
         K = _gather(inputs, ("K", src_scale), n_seq, cache)
         inv_K = _gather(inputs, ("inv_K", src_scale), n_seq, cache)
         srcs = [_gather(inputs, ("color", f, src_scale), n_seq, cache) for f in sources]
-        disps, colors, weights = [], [], []
+        disps, colors, weights, fws, bces = [], [], [], [], []
         for s in group:
             disps.append(outputs[("disp", s)])
+            if pmask:
+                # trainer.py:573-583: resize the mask unless v1_multiscale, weight the reprojection
+                # losses with it, and push it towards 1 with 0.2 * BCE(mask, ones)
+                mask = outputs["predictive_mask"][("disp", s)]
+                if not opt.v1_multiscale:
+                    mask = _L.interpolate_bilinear(mask, [H, W])
+                fws.append(mask)
+                bces.append(0.2 * _F.bce_against_ones(mask))
             # trainer.py:547 smooths against the colour at the disparity's own scale;
             # trainer_fusion.py:504 against source_scale (its disparities are full-res)
             cs = src_scale if variant == "fusion" else s
@@ -126,9 +134,9 @@ def _run_fused(self, inputs, outputs):
             min_depth=opt.min_depth, max_depth=opt.max_depth, no_ssim=opt.no_ssim,
             disable_automasking=opt.disable_automasking, avg_reprojection=opt.avg_reprojection,
             noise=[noise[s] for s in group] if noise else None, seed=seed + 7919 * scales.index(group[0]),
-            emit_depth=ed, emit_warped=ew)
+            emit_depth=ed, emit_warped=ew, frame_weights=fws if pmask else None)
         for i, s in enumerate(group):
-            res["loss"][s] = out["loss"][i]
+            res["loss"][s] = out["loss"][i] + bces[i] if pmask else out["loss"][i]
             res["terms"][s] = out["terms"][i]
             res["argmin"][s] = out["argmin"][i]
             if i in out["depth"]:

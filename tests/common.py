@@ -59,11 +59,17 @@ def run_product(opt, inputs, outputs, variant="trainer", device="cuda", noise_se
     if variant == "gru":
         inp = synthetic.to_sequence_layout(inp, opt.len_sequence)
     out = {k: v.to(dev).clone() for k, v in outputs.items()}
+    flat = [k for k in out if isinstance(k, tuple) and k[0] == "predictive_mask"]
+    if flat:   # the trainers read outputs["predictive_mask"]["disp", s] (trainer.py:573)
+        out["predictive_mask"] = {("disp", k[1]): out.pop(k) for k in flat}
     leaves = {}
     if want_grad:
         for s in opt.scales:
             out[("disp", s)].requires_grad_(True)
             leaves["grad_disp/%d" % s] = out[("disp", s)]
+            if "predictive_mask" in out:
+                out["predictive_mask"][("disp", s)].requires_grad_(True)
+                leaves["grad_mask/%d" % s] = out["predictive_mask"][("disp", s)]
         for f in sources:
             if f != "s":
                 out[("cam_T_cam", 0, f)].requires_grad_(True)

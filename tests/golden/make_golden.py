@@ -38,6 +38,9 @@ CASES = {
     "fusion_default":       ("fusion", {}, dict(style="kitti", seed=21, full_res_disp=True)),
     "fusion_v3_default":    ("fusion_v3", {}, dict(style="kitti", seed=22)),
     "gru_seq3":             ("gru", dict(len_sequence=3, batch_size=1), dict(style="kitti", seed=23, batch=3)),
+    "trainer_predmask":     ("trainer", dict(disable_automasking=True, predictive_mask=True), dict(style="kitti", seed=25, predictive_mask=True)),
+    "trainer_predmask_avg": ("trainer", dict(disable_automasking=True, predictive_mask=True, avg_reprojection=True),
+                             dict(style="kitti", seed=26, predictive_mask=True)),
     "trainer_wide":         ("trainer", {}, dict(style="kitti", seed=24, batch=1, height=64, width=160)),
 }
 NOISE_SEED = 1234

@@ -79,6 +79,28 @@ def run(device, B=2, H=16, W=24):
         assert err(M.detach().cpu(), M64.detach()) < 1e-6
         assert err(aa.grad.cpu(), aa64.grad) < 1e-4 and err(tr.grad.cpu(), tr64.grad) < 1e-5
 
+    # F.interpolate bilinear, align_corners=False (trainer.py:474-475, :574-576) incl. non-integer ratios
+    for (h, w, Hh, Ww) in ((H // 2, W // 2, H, W), (H // 8, W // 8, H, W), (5, 7, 16, 24), (H, W, H, W)):
+        xs, xs64 = _leaf(torch.rand(B, 2, h, w, generator=g), dev)
+        wgt = torch.randn(B, 2, Hh, Ww, generator=g)
+        up = L.interpolate_bilinear(xs, [Hh, Ww])
+        up64 = torch.nn.functional.interpolate(xs64, [Hh, Ww], mode="bilinear", align_corners=False)
+        (up * wgt.to(dev)).sum().backward()
+        (up64 * wgt.double()).sum().backward()
+        assert up.shape == (B, 2, Hh, Ww)
+        assert err(up.detach().cpu(), up64.detach()) < 1e-6
+        assert err(xs.grad.cpu(), xs64.grad) < 1e-5
+
+    # nn.BCELoss()(mask, ones) (trainer.py:582)
+    from ssde_b200 import functional as Fn
+    m, m64 = _leaf(torch.sigmoid(3 * torch.randn(B, 2, H, W, generator=g)), dev)
+    bce = Fn.bce_against_ones(m)
+    bce64 = torch.nn.functional.binary_cross_entropy(m64, torch.ones_like(m64))
+    (bce * 0.2).backward()
+    (bce64 * 0.2).backward()
+    assert bce.dim() == 0 and err(bce.detach().cpu(), bce64.detach()) < 1e-6
+    assert err(m.grad.cpu(), m64.grad) < 1e-5
+
 
 def depth_metrics(device):
     """functional.depth_metrics / trainer_hooks.compute_depth_losses against the float64 oracle on the

@@ -40,7 +40,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_struct_layout_matches_header():
     # offsets implied by include/pml.h on LP64
-    assert ctypes.sizeof(_cabi.PmlPass) == 16 + 7 * 8
+    assert ctypes.sizeof(_cabi.PmlPass) == 16 + 9 * 8
     assert _cabi.PmlProblem.seed.offset == 40
     assert _cabi.PmlProblem.target.offset == 48
     assert _cabi.PmlProblem.passes.offset == 48 + 8 * (1 + 4 + 2 + 4)

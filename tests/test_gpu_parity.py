@@ -34,6 +34,13 @@ CONFIGS = {
     "single_scale3": dict(B=2, H=64, W=96, sources=(1,), variant="trainer", style="kitti", scales=[3]),
     "four_sources_avg": dict(B=1, H=64, W=160, sources=(-1, 1, -2, 2), variant="trainer", style="kitti",
                              opt=dict(avg_reprojection=True)),
+    # --predictive_mask ablation (trainer.py:571-583): two frames, three frames with stereo, v1_multiscale
+    "predictive_mask": dict(B=2, H=96, W=320, sources=(-1, 1), variant="trainer", style="kitti", pmask=True,
+                            opt=dict(disable_automasking=True, predictive_mask=True)),
+    "predictive_mask_stereo": dict(B=1, H=96, W=320, sources=(-1, 1, "s"), variant="trainer", style="kitti", pmask=True,
+                                   opt=dict(disable_automasking=True, predictive_mask=True)),
+    "predictive_mask_v1": dict(B=2, H=64, W=160, sources=(-1, 1), variant="trainer", style="kitti", pmask=True,
+                               opt=dict(disable_automasking=True, predictive_mask=True, v1_multiscale=True)),
 }
 
 
@@ -46,7 +53,8 @@ def test_against_oracle(cuda_lib, name):
         kw["scales"] = c["scales"]
     opt = synthetic.make_options(H, W, batch_size=B, len_sequence=c.get("len_sequence", 1), **kw)
     inputs, outputs = synthetic.make_batch(B, H, W, sources=sources, seed=31, style=c["style"],
-                                           full_res_disp=(variant == "fusion"), scales=opt.scales)
+                                           full_res_disp=(variant == "fusion"), scales=opt.scales,
+                                           predictive_mask=c.get("pmask", False))
     if c.get("neg_disp"):
         # Fusion's UpscalePS ends in tanh (fusion_v2.py:234-235): disparities are not confined to
         # [0,1]; keep sigma > 0 so that depth stays finite in the oracle too
