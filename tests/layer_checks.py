@@ -88,7 +88,8 @@ def run(device, B=2, H=16, W=24):
         (up * wgt.to(dev)).sum().backward()
         (up64 * wgt.double()).sum().backward()
         assert up.shape == (B, 2, Hh, Ww)
-        assert err(up.detach().cpu(), up64.detach()) < 1e-6
+        # fp32 source coordinates (ATen computes them in fp32 too): ~ulp(scale) * size * slope
+        assert err(up.detach().cpu(), up64.detach()) < 3e-6
         assert err(xs.grad.cpu(), xs64.grad) < 1e-5
 
     # nn.BCELoss()(mask, ones) (trainer.py:582)
