@@ -238,16 +238,29 @@ def run_ours(args, rank, world, dev):
                 "step_frac_of_peak": round(synthetic.algorithmic_bytes(args.batch, args.height, args.width, S, n)
                                            / (ms_total / K * 1e-3) / 1e9 / peak, 4)}
 
-    # ---- end-to-end arm: Trainer drop-ins, pinned host inputs, H2D + D2H inside the region --
-    e2e = None
-    if not args.no_e2e:
+    # ---- end-to-end arms: Trainer drop-ins, pinned host inputs, H2D + D2H inside the region --
+    # "fp32": the strict drop-in -- the host holds what the reference's DataLoader yields (fp32 colour
+    #         pyramids of all frames, mono_dataset.py:99-111) and uploads them like trainer.py:233-237.
+    # "u8":   SURVEY 8 row f1 -- the host holds the uint8 scale-0 frames (what the image decoder
+    #         delivers); trainer_hooks.ingest_colors builds the fp32 pyramid on the device (bit-exact with
+    #         PIL + ToTensor), so a quarter of the colour bytes cross the PCIe link.
+    e2e, e2e_u8 = None, None
+
+    def e2e_arm(mode):
         o2 = SimpleNamespace(**vars(opt))
         o2.pml_sources, o2.pml_variant, o2.pml_noise = srcs, "trainer", "philox"
         o2.pml_emit_depth, o2.pml_emit_selection = "scale0", True
         ns = SimpleNamespace(opt=o2, device=dev, num_scales=len(opt.scales))
+        frames = [0] + list(srcs)
         host = []
         for (i, o) in sets:
-            hi = {k: v.pin_memory() for k, v in i.items() if not (isinstance(k, tuple) and k[0] == "color" and k[1] != 0 and k[2] != 0)}
+            if mode == "u8":
+                hi = {("color_u8", f): (i[("color", f, 0)].permute(0, 2, 3, 1) * 255.0).round().clamp(0, 255)
+                      .to(torch.uint8).contiguous().pin_memory() for f in frames}
+                hi.update({k: v.pin_memory() for k, v in i.items() if not (isinstance(k, tuple) and k[0] == "color")})
+            else:
+                hi = {k: v.pin_memory() for k, v in i.items()
+                      if not (isinstance(k, tuple) and k[0] == "color" and k[1] != 0 and k[2] != 0)}
             ho = {k: v.pin_memory() for k, v in o.items() if k[0] in ("disp", "cam_T_cam")}
             host.append((hi, ho))
         h2d = sum(v.numel() * v.element_size() for v in list(host[0][0].values()) + list(host[0][1].values()))
@@ -272,6 +285,8 @@ def run_ours(args, rank, world, dev):
                 v.record_stream(main_stream)
             for k, v in out.items():
                 v.requires_grad_(True)
+            if mode == "u8":
+                trainer_hooks.ingest_colors(inp, frames, len(opt.scales), device=dev)
             trainer_hooks.generate_images_pred(ns, inp, out)
             losses = trainer_hooks.compute_losses(ns, inp, out)
             losses["loss"].backward()
@@ -298,11 +313,17 @@ def run_ours(args, rank, world, dev):
         t = torch.tensor([dt], device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": round(world * n_pix * Ke / t.item() / 1e6, 2), "unit": UNIT,
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4, "steps": Ke,
-               "ms_per_step": round(t.item() / Ke * 1e3, 4),
-               "api": "trainer_hooks.generate_images_pred + compute_losses + loss.backward(); pinned-host inputs, "
-                      "H2D of step i+1 overlapped with the kernels of step i (copy stream), loss.item() every step"}
+        api = "trainer_hooks.generate_images_pred + compute_losses + loss.backward(); pinned-host inputs, " \
+              "H2D of step i+1 overlapped with the kernels of step i (copy stream), loss.item() every step"
+        if mode == "u8":
+            api = "trainer_hooks.ingest_colors (uint8 scale-0 frames -> fp32 pyramid on the device) + " + api
+        return {"value": round(world * n_pix * Ke / t.item() / 1e6, 2), "unit": UNIT,
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4, "steps": Ke,
+                "ms_per_step": round(t.item() / Ke * 1e3, 4), "api": api}
+
+    if not args.no_e2e:
+        e2e = e2e_arm("fp32")
+        e2e_u8 = e2e_arm("u8")
 
     res = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
            "ms_per_step": round(ms_total / K, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -311,7 +332,7 @@ def run_ours(args, rank, world, dev):
                           l2="rotating %d input sets (%.0f MB in total > 126 MB L2): every step starts L2-cold"
                              % (len(sets), len(sets) * set_mb),
                           timing="CUDA events around K CUDA-graph replays, max over ranks"),
-           "clocks": clk, "e2e": e2e, "gpu_launches": kernels_per_step * K, "roofline": roofline}
+           "clocks": clk, "e2e": e2e, "e2e_u8_ingest": e2e_u8, "gpu_launches": kernels_per_step * K, "roofline": roofline}
     return res
 
 

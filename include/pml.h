@@ -150,6 +150,16 @@ int pml_bce_ones_fwd(const float* mask, int64_t n, float* out, void* workspace, 
 int pml_bce_ones_bwd(const float* mask, const float* g_out, float* g_mask, int64_t n, pml_stream_t);
 
 
+/* ---- input colour pyramid: datasets/mono_dataset.py:84-111 resizes every
+ * frame on the CPU with PIL (scale i = Resize((H >> i, W >> i), Image.ANTIALIAS) of scale i-1), applies
+ * ToTensor and the trainer uploads all scales as fp32 (trainer.py:233-237).  Here the caller uploads the
+ * uint8 scale-0 frames [N,H,W,3] (PIL / numpy layout) and gets out[s] = fp32 [N,3,H>>s,W>>s] for
+ * s = 0..n_scales-1, bit-exact with Pillow's 8-bit Lanczos resampling + torchvision's ToTensor.  `out` is
+ * a HOST array of n_scales device pointers; H and W must be multiples of 2^(n_scales-1). ---- */
+size_t pml_pyramid_workspace_bytes(int32_t N, int32_t H, int32_t W, int32_t n_scales);
+int pml_pyramid_u8(const uint8_t* frames, int32_t N, int32_t H, int32_t W, int32_t n_scales, float* const* out,
+                   void* workspace, size_t workspace_bytes, pml_stream_t);
+
 /* ---- monitoring metrics: Trainer.compute_depth_losses (trainer.py:624-652) over
  * layers.compute_depth_errors (layers.py:251-269).  prepare resizes depth [B,1,H,W] to the ground
  * truth's [B,1,Hg,Wg] (bilinear, align_corners=False), clamps, applies mask = gt>0 & crop and writes

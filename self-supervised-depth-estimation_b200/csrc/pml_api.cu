@@ -8,7 +8,9 @@
 #include "pml_layers.cuh"
 #include "pml_metrics.cuh"
 #include "pml_mask.cuh"
+#include "pml_pyramid.cuh"
 
+#include <math.h>
 #include <stdlib.h>
 #include <atomic>
 
@@ -171,7 +173,7 @@ int launch_photo(const PhotoParams& pp, int n_cta, int NT, int low_cells, cudaSt
 
 template <bool GRAD, bool SSIM>
 int launch_sweep(const PhotoParams& pp, cudaStream_t st) {
-    const size_t smem = sweep_smem_bytes();   // < 48 KB: no opt-in needed
+    const size_t smem = sweep_smem_bytes() + (size_t)env_int("PML_SMEM_PAD", 0);   // < 48 KB: no opt-in needed
     if (pp.B > 65535) return PML_ERR_UNSUPPORTED;
     const dim3 grid(pp.n_chunks * pp.n_strips, pp.B, pp.n_pass);
     PML_LAUNCH((sweep_kernel<GRAD, SSIM>), grid, dim3(kSweepWarps * 32), smem, st, pp);

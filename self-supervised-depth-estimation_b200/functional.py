@@ -465,6 +465,29 @@ def bce_against_ones(mask: torch.Tensor) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------
+# input colour pyramid (datasets/mono_dataset.py:84-111)
+# ------------------------------------------------------------------------------------------------
+def color_pyramid(frames_u8: torch.Tensor, n_scales: int = 4) -> List[torch.Tensor]:
+    """uint8 scale-0 frames [N,H,W,3] (PIL / numpy layout, on the device) -> list over scales of
+    fp32 [N,3,H>>s,W>>s]: what ``MonoDataset.preprocess`` + ``ToTensor`` produce on the CPU for
+    ``("color", f, s)``, bit for bit (Pillow 8-bit Lanczos chain, value / 255)."""
+    lib = get_library()
+    if frames_u8.dtype != torch.uint8 or frames_u8.dim() != 4 or frames_u8.shape[3] != 3:
+        raise TypeError("frames must be uint8 [N,H,W,3]")
+    if not frames_u8.is_cuda and not lib.emulator:
+        raise RuntimeError("frames are on %s: libpml has no CPU path, move them to a CUDA device" % frames_u8.device)
+    frames_u8 = frames_u8.contiguous()
+    N, H, W, _ = frames_u8.shape
+    outs = [torch.empty((N, 3, H >> s, W >> s), device=frames_u8.device, dtype=torch.float32) for s in range(n_scales)]
+    nb = lib.pml_pyramid_workspace_bytes(N, H, W, n_scales)
+    ws = torch.empty(nb, device=frames_u8.device, dtype=torch.uint8)
+    ptrs = (ctypes.c_void_p * n_scales)(*[o.data_ptr() for o in outs])
+    lib.check(lib.pml_pyramid_u8(_ptr(frames_u8), N, H, W, n_scales, ptrs, _ptr(ws), nb, _stream_ptr(frames_u8)),
+              "pml_pyramid_u8")
+    return outs
+
+
+# ------------------------------------------------------------------------------------------------
 # monitoring metrics (trainer.py:624-652, layers.py:251-269)
 # ------------------------------------------------------------------------------------------------
 GARG_CROP_375x1242 = (153, 371, 44, 1197)   # trainer.py:641: crop_mask[:, :, 153:371, 44:1197] = 1
