@@ -24,8 +24,10 @@ namespace pml {
 
 constexpr int kResampleTaps = 13;      // ksize = ceil(3 * 2) * 2 + 1 for a 2x reduction
 constexpr int kResampleBits = 22;      // Resample.c PRECISION_BITS = 32 - 8 - 2
-constexpr int kPyrTOH = 8, kPyrTOW = 32;                       // output tile of one CTA
-constexpr int kPyrIH = 2 * kPyrTOH + 10, kPyrIW = 2 * kPyrTOW + 10;   // parent pixels under it
+constexpr int kPyrTOH = 16, kPyrTOW = 32;                      // output tile of one CTA (256 threads)
+constexpr int kPyrIH = 2 * kPyrTOH + 10, kPyrIW = 2 * kPyrTOW + 10;   // parent pixels under it: 42 x 74
+constexpr int kPyrRowWords = 64;       // staged parent row: <= 74 * 3 + 3 bytes, word aligned
+constexpr int kPyrTmpStride = kPyrTOW * 3 + 4;
 
 // Coefficient sets of one axis: set 0..2 = outputs 0..2, set 3 = every interior output
 // (xmin = 2 * xx - 5, 12 taps), set 4..6 = outputs out-3 .. out-1.
@@ -46,63 +48,114 @@ struct PyramidLevelParams {
 __device__ __forceinline__ int resample_set(int xx, int out) { return xx < 3 ? xx : (xx > out - 4 ? 4 + xx - (out - 3) : 3); }
 __device__ __forceinline__ int clip8(int acc) { return min(max(acc >> kResampleBits, 0), 255); }
 
+// One output sample of one pass: `src` points at tap 0 of the interior window (which may lie
+// outside the staged data for the cut windows at the image border -- those use their own first tap).
+template <int STRIDE>
+__device__ __forceinline__ int resample_sample(const uint8_t* src, int xx, int first_interior, const ResampleAxis& a,
+                                               const int (&kin)[12]) {
+    const int set = resample_set(xx, a.out);
+    int acc = 1 << (kResampleBits - 1);
+    if (set == 3) {
+#pragma unroll
+        for (int t = 0; t < 12; ++t) acc += (int)src[t * STRIDE] * kin[t];
+    } else {
+        const uint8_t* sb = src + (a.xmin[set] - first_interior) * STRIDE;
+        const int cnt = a.cnt[set];
+        for (int t = 0; t < cnt; ++t) acc += (int)sb[t * STRIDE] * a.k[set][t];
+    }
+    return clip8(acc);
+}
+
 __global__ void __launch_bounds__(256)
 pyramid_level_kernel(const PyramidLevelParams q) {
-    __shared__ uint8_t s_in[kPyrIH][kPyrIW * 3 + 2];
-    __shared__ uint8_t s_tmp[kPyrIH][kPyrTOW * 3];
+    __shared__ uint32_t s_in[kPyrIH][kPyrRowWords];          // parent window, HWC bytes, rows word aligned
+    __shared__ uint8_t s_tmp[kPyrIH][kPyrTmpStride];         // after the horizontal pass
+    __shared__ float s_div[256];                             // ToTensor: v / 255, IEEE division
+    const int tid = threadIdx.x;
     const int n = blockIdx.z, oy0 = blockIdx.y * kPyrTOH, ox0 = blockIdx.x * kPyrTOW;
     const int h = q.ay.out, w = q.ax.out, ph = q.ay.in, pw = q.ax.in;
-    // parent window under this tile (clamped to the image: the border coefficient sets never
-    // reach outside, so the clamped rows / columns are simply never read)
+    s_div[tid] = __fdiv_rn((float)tid, 255.0f);
+    // parent window under this tile, clamped to the image (the cut border windows never reach outside)
     const int iy0 = max(2 * oy0 - 5, 0), ix0 = max(2 * ox0 - 5, 0);
     const int iy1 = min(2 * (oy0 + kPyrTOH - 1) + 7, ph), ix1 = min(2 * (ox0 + kPyrTOW - 1) + 7, pw);
-    const int nrow = iy1 - iy0, nbyte = (ix1 - ix0) * 3;
+    const int nrow = iy1 - iy0;
     const uint8_t* src = q.parent + ((size_t)n * ph * pw) * 3;
-    for (int i = threadIdx.x; i < nrow * nbyte; i += 256) {
-        const int r = i / nbyte, c = i - r * nbyte;
-        s_in[r][c] = __ldg(src + ((size_t)(iy0 + r) * pw + ix0) * 3 + c);
+    {   // aligned 32-bit loads: 4 rows per pass, 64 words per row (tensor bases are 16-byte aligned and
+        // their sizes multiples of 4, so an aligned word never leaves the tensor)
+        const int wi = tid & 63;
+        for (int r = tid >> 6; r < nrow; r += 4) {
+            const uintptr_t a0 = reinterpret_cast<uintptr_t>(src + ((size_t)(iy0 + r) * pw + ix0) * 3);
+            const uintptr_t a1 = reinterpret_cast<uintptr_t>(src + ((size_t)(iy0 + r) * pw + ix1) * 3);
+            const uint32_t* wp = reinterpret_cast<const uint32_t*>(a0 & ~(uintptr_t)3) + wi;
+            if (reinterpret_cast<uintptr_t>(wp) < a1) s_in[r][wi] = __ldg(wp);
+        }
     }
     __syncthreads();
-    // horizontal pass: (parent rows of the window) x (tile columns) x 3 channels -> uint8
-    const int tw = min(kPyrTOW, w - ox0);
-    for (int i = threadIdx.x; i < nrow * tw * 3; i += 256) {
-        const int r = i / (tw * 3), rem = i - r * (tw * 3), ox = rem / 3, ch = rem - ox * 3;
-        const int xx = ox0 + ox, set = resample_set(xx, w);
-        const int xmin = (set == 3) ? 2 * xx - 5 : q.ax.xmin[set];
-        const int cnt = q.ax.cnt[set];
-        int acc = 1 << (kResampleBits - 1);
-        for (int t = 0; t < cnt; ++t) acc += (int)s_in[r][(xmin - ix0 + t) * 3 + ch] * q.ax.k[set][t];
-        s_tmp[r][ox * 3 + ch] = (uint8_t)clip8(acc);
+    int kin[12];
+#pragma unroll
+    for (int t = 0; t < 12; ++t) kin[t] = q.ax.k[3][t];      // interior set (identical for both axes)
+    const int tw = min(kPyrTOW, w - ox0), th = min(kPyrTOH, h - oy0);
+    const int ox = tid & 31;
+    // horizontal pass: every staged parent row x tile columns x 3 channels -> uint8
+    if (ox < tw) {
+        const int xx = ox0 + ox;
+        for (int r = tid >> 5; r < nrow; r += 8) {
+            const uintptr_t a0 = reinterpret_cast<uintptr_t>(src + ((size_t)(iy0 + r) * pw + ix0) * 3);
+            const uint8_t* row = reinterpret_cast<const uint8_t*>(&s_in[r][0]) + (a0 & 3);
+            const uint8_t* p0 = row + (2 * xx - 5 - ix0) * 3;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch)
+                s_tmp[r][ox * 3 + ch] = (uint8_t)resample_sample<3>(p0 + ch, xx, 2 * xx - 5, q.ax, kin);
+        }
     }
     __syncthreads();
     // vertical pass + ToTensor
-    const int th = min(kPyrTOH, h - oy0);
-    for (int i = threadIdx.x; i < th * tw * 3; i += 256) {
-        const int ch = i / (th * tw), rem = i - ch * (th * tw), oy = rem / tw, ox = rem - oy * tw;
-        const int yy = oy0 + oy, set = resample_set(yy, h);
-        const int ymin = (set == 3) ? 2 * yy - 5 : q.ay.xmin[set];
-        const int cnt = q.ay.cnt[set];
-        int acc = 1 << (kResampleBits - 1);
-        for (int t = 0; t < cnt; ++t) acc += (int)s_tmp[ymin - iy0 + t][ox * 3 + ch] * q.ay.k[set][t];
-        const int v = clip8(acc);
+    if (ox < tw) {
         const int xx = ox0 + ox;
-        if (q.child) q.child[(((size_t)n * h + yy) * w + xx) * 3 + ch] = (uint8_t)v;
-        q.child_f[(((size_t)n * 3 + ch) * h + yy) * w + xx] = __fdiv_rn((float)v, 255.0f);
+        for (int oy = tid >> 5; oy < th; oy += 8) {
+            const int yy = oy0 + oy;
+            const uint8_t* p0 = &s_tmp[0][ox * 3] + (2 * yy - 5 - iy0) * kPyrTmpStride;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const int v = resample_sample<kPyrTmpStride>(p0 + ch, yy, 2 * yy - 5, q.ay, kin);
+                if (q.child) q.child[(((size_t)n * h + yy) * w + xx) * 3 + ch] = (uint8_t)v;
+                q.child_f[(((size_t)n * 3 + ch) * h + yy) * w + xx] = s_div[v];
+            }
+        }
     }
 }
 
-// scale 0: ToTensor only.  frames [N,H,W,3] uint8 -> out [N,3,H,W] fp32
+// scale 0: ToTensor only.  frames [N,H,W,3] uint8 -> out [N,3,H,W] fp32; one thread per 4 pixels
+// (three aligned words in, three float4 out) when H*W is a multiple of 4, else one per pixel.
 __global__ void __launch_bounds__(256)
-to_tensor_kernel(const uint8_t* __restrict__ frames, float* __restrict__ out, int HW, long long total) {
-    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;   // one thread per pixel
-    if (i >= total) return;
-    const long long n = i / HW;
-    const int p = (int)(i - n * HW);
-    const uint8_t* s = frames + i * 3;
-    float* d = out + n * 3 * HW + p;
-    d[0] = __fdiv_rn((float)__ldg(s), 255.0f);
-    d[HW] = __fdiv_rn((float)__ldg(s + 1), 255.0f);
-    d[2 * HW] = __fdiv_rn((float)__ldg(s + 2), 255.0f);
+to_tensor_kernel(const uint8_t* __restrict__ frames, float* __restrict__ out, int HW, long long total, int vec) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (vec) {
+        const long long p4 = i * 4;
+        if (p4 >= total) return;
+        const long long n = p4 / HW;
+        const int p = (int)(p4 - n * HW);
+        const uint32_t* s = reinterpret_cast<const uint32_t*>(frames + p4 * 3);
+        const uint32_t w0 = __ldg(s), w1 = __ldg(s + 1), w2 = __ldg(s + 2);
+        // bytes: r0 g0 b0 r1 | g1 b1 r2 g2 | b2 r3 g3 b3
+        float* d = out + n * 3 * HW + p;
+        const float k = 255.0f;
+        *reinterpret_cast<float4*>(d) = make_float4(__fdiv_rn((float)(w0 & 255u), k), __fdiv_rn((float)(w0 >> 24), k),
+                                                    __fdiv_rn((float)((w1 >> 16) & 255u), k), __fdiv_rn((float)((w2 >> 8) & 255u), k));
+        *reinterpret_cast<float4*>(d + HW) = make_float4(__fdiv_rn((float)((w0 >> 8) & 255u), k), __fdiv_rn((float)(w1 & 255u), k),
+                                                         __fdiv_rn((float)(w1 >> 24), k), __fdiv_rn((float)((w2 >> 16) & 255u), k));
+        *reinterpret_cast<float4*>(d + 2 * HW) = make_float4(__fdiv_rn((float)((w0 >> 16) & 255u), k), __fdiv_rn((float)((w1 >> 8) & 255u), k),
+                                                             __fdiv_rn((float)(w2 & 255u), k), __fdiv_rn((float)(w2 >> 24), k));
+    } else {
+        if (i >= total) return;
+        const long long n = i / HW;
+        const int p = (int)(i - n * HW);
+        const uint8_t* s = frames + i * 3;
+        float* d = out + n * 3 * HW + p;
+        d[0] = __fdiv_rn((float)__ldg(s), 255.0f);
+        d[HW] = __fdiv_rn((float)__ldg(s + 1), 255.0f);
+        d[2 * HW] = __fdiv_rn((float)__ldg(s + 2), 255.0f);
+    }
 }
 
 }  // namespace pml
