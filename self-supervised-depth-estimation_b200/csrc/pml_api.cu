@@ -176,7 +176,9 @@ int launch_sweep(const PhotoParams& pp, cudaStream_t st) {
     const size_t smem = sweep_smem_bytes() + (size_t)env_int("PML_SMEM_PAD", 0);   // < 48 KB: no opt-in needed
     if (pp.B > 65535) return PML_ERR_UNSUPPORTED;
     const dim3 grid(pp.n_chunks * pp.n_strips, pp.B, pp.n_pass);
-    PML_LAUNCH((sweep_kernel<GRAD, SSIM>), grid, dim3(kSweepWarps * 32), smem, st, pp);
+    if (pp.mode == 0)      PML_LAUNCH((sweep_kernel<GRAD, SSIM, 0>), grid, dim3(kSweepWarps * 32), smem, st, pp);
+    else if (!GRAD)        PML_LAUNCH((sweep_kernel<false, SSIM, 1>), grid, dim3(kSweepWarps * 32), smem, st, pp);
+    else                   PML_LAUNCH((sweep_kernel<true, SSIM, 2>), grid, dim3(kSweepWarps * 32), smem, st, pp);
     return PML_OK;
 }
 

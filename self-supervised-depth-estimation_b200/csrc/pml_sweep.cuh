@@ -138,7 +138,8 @@ __device__ __noinline__ void sweep_flush_row(float* sG, float* gd_row, float h, 
     __syncwarp();
 }
 
-template <bool GRAD, bool SSIM>
+// MODE (see PhotoParams::mode): 0 selection in the sweep; 1 reprojection losses only; 2 selection given.
+template <bool GRAD, bool SSIM, int MODE>
 __global__ void __launch_bounds__(kSweepWarps * 32)
 sweep_kernel(const PhotoParams p) {
     PML_DYN_SMEM(float, smem);
@@ -162,7 +163,7 @@ sweep_kernel(const PhotoParams p) {
 
     const bool automask = !(p.flags & PML_FLAG_NO_AUTOMASK);
     const bool avg = (p.flags & PML_FLAG_AVG_REPROJ) != 0;
-    const int mode = p.mode;                              // see PhotoParams::mode
+    constexpr int mode = MODE;
     const int n_sel = automask ? (avg ? 1 : S) : 0;       // identity candidates of the selection
     const int n_id = (mode == 0) ? n_sel : 0;             // ... evaluated by this launch
     const int fa = p.f_base;                              // frames in the two halves of every pair
