@@ -176,9 +176,22 @@ int launch_sweep(const PhotoParams& pp, cudaStream_t st) {
     const size_t smem = sweep_smem_bytes() + (size_t)env_int("PML_SMEM_PAD", 0);   // < 48 KB: no opt-in needed
     if (pp.B > 65535) return PML_ERR_UNSUPPORTED;
     const dim3 grid(pp.n_chunks * pp.n_strips, pp.B, pp.n_pass);
-    if (pp.mode == 0)      PML_LAUNCH((sweep_kernel<GRAD, SSIM, 0>), grid, dim3(kSweepWarps * 32), smem, st, pp);
-    else if (!GRAD)        PML_LAUNCH((sweep_kernel<false, SSIM, 1>), grid, dim3(kSweepWarps * 32), smem, st, pp);
-    else                   PML_LAUNCH((sweep_kernel<true, SSIM, 2>), grid, dim3(kSweepWarps * 32), smem, st, pp);
+    bool emit = false;   // by-products requested by any pass (never in sweep mode 2)
+    for (int i = 0; i < pp.n_pass; ++i) emit = emit || pp.pass[i].depth != nullptr || pp.pass[i].warped != nullptr;
+    const dim3 blk(kSweepWarps * 32);
+    bool common = pp.mode == 0 && !emit && pp.S == 2 && !(pp.flags & (PML_FLAG_NO_AUTOMASK | PML_FLAG_AVG_REPROJ));
+    for (int i = 0; i < pp.n_pass; ++i) common = common && pp.pass[i].noise == nullptr;
+    if (common) {
+        PML_LAUNCH((sweep_kernel<GRAD, SSIM, 0, false, true>), grid, blk, smem, st, pp);
+    } else if (pp.mode == 0) {
+        if (emit) PML_LAUNCH((sweep_kernel<GRAD, SSIM, 0, true>), grid, blk, smem, st, pp);
+        else      PML_LAUNCH((sweep_kernel<GRAD, SSIM, 0, false>), grid, blk, smem, st, pp);
+    } else if (!GRAD) {
+        if (emit) PML_LAUNCH((sweep_kernel<false, SSIM, 1, true>), grid, blk, smem, st, pp);
+        else      PML_LAUNCH((sweep_kernel<false, SSIM, 1, false>), grid, blk, smem, st, pp);
+    } else {
+        PML_LAUNCH((sweep_kernel<true, SSIM, 2, false>), grid, blk, smem, st, pp);
+    }
     return PML_OK;
 }
 
