@@ -183,7 +183,7 @@ def run_ours(args, rank, world, dev):
                 keep = st()
         graphs.append((g, keep))
     torch.cuda.synchronize()
-    kernels_per_step = 7   # disp_sum, smooth_sweep, identity_sweep, sweep, finalize_image, finalize_loss, scale_grads
+    kernels_per_step = 6   # disp_sum, prep (identity + smoothness sweeps), sweep, finalize_image, finalize_loss, scale_grads
     for i in range(max(W, 3)):
         graphs[i % len(graphs)][0].replay()
     barrier()

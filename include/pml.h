@@ -93,6 +93,7 @@ typedef struct pml_problem {
                                (gradient through disp.mean(), trainer.py:612)  (forward_backward) */
     void* prof_start;       /* optional cudaEvent_t recorded right before the fused sweep kernel */
     void* prof_stop;        /* optional cudaEvent_t recorded right after it (bench.py roofline) */
+    float* loss_vector;     /* [n_pass] out, nullable: loss_s again as a contiguous vector (what autograd returns) */
 } pml_problem;
 
 int pml_abi_version(void);

@@ -34,7 +34,7 @@ class PmlProblem(Structure):
                 ("K", c_void_p), ("inv_K", c_void_p), ("T", c_void_p * PML_MAX_SOURCES),
                 ("passes", PmlPass * PML_MAX_PASSES),
                 ("losses", c_void_p), ("grad_T", c_void_p), ("grad_disp_const", c_void_p),
-                ("prof_start", c_void_p), ("prof_stop", c_void_p)]
+                ("prof_start", c_void_p), ("prof_stop", c_void_p), ("loss_vector", c_void_p)]
 
 
 class PmlError(RuntimeError):

@@ -234,10 +234,13 @@ int run_loss(const pml_problem* p, void* ws, size_t ws_bytes, cudaStream_t st, b
         sp.pass[i].weight = ps.smooth_weight;
     }
     PML_LAUNCH(disp_sum_kernel, dim3(pl.max_chunks, p->B, p->n_pass), dim3(256), 0, st, sp);
-    if (pl.sweep) {
+    // warp-strip path with automask: the smoothness sweep shares one launch with the identity sweep of
+    // the first frame pair (prep_kernel); otherwise it is launched on its own
+    const bool merged_prep = pl.sweep && pl.n_id > 0;
+    if (pl.sweep && !merged_prep) {
         if (grad) PML_LAUNCH(smooth_sweep_kernel<true>, dim3(pl.smooth_total), dim3(32), 0, st, sp);
         else      PML_LAUNCH(smooth_sweep_kernel<false>, dim3(pl.smooth_total), dim3(32), 0, st, sp);
-    } else {
+    } else if (!pl.sweep) {
         if (grad) PML_LAUNCH(smooth_kernel<true>, dim3(pl.smooth_total), dim3(256), 0, st, sp);
         else      PML_LAUNCH(smooth_kernel<false>, dim3(pl.smooth_total), dim3(256), 0, st, sp);
     }
@@ -256,8 +259,15 @@ int run_loss(const pml_problem* p, void* ws, size_t ws_bytes, cudaStream_t st, b
             ip.n_strips = (p->W + kPrepTW - 1) / kPrepTW;
             ip.n_chunks = (p->H + ip.TH - 1) / ip.TH;
             const dim3 g(ip.n_chunks * ip.n_strips, p->B);
-            if (ssim) PML_LAUNCH(identity_sweep_kernel<true>, g, dim3(32), 0, st, ip);
-            else      PML_LAUNCH(identity_sweep_kernel<false>, g, dim3(32), 0, st, ip);
+            if (fa == 0) {
+                const int n_items = ip.n_chunks * ip.n_strips * p->B;
+                const dim3 gm(n_items + pl.smooth_total);
+                if (ssim) { if (grad) PML_LAUNCH((prep_kernel<true, true>), gm, dim3(32), 0, st, ip, sp, n_items);
+                            else      PML_LAUNCH((prep_kernel<true, false>), gm, dim3(32), 0, st, ip, sp, n_items); }
+                else      { if (grad) PML_LAUNCH((prep_kernel<false, true>), gm, dim3(32), 0, st, ip, sp, n_items);
+                            else      PML_LAUNCH((prep_kernel<false, false>), gm, dim3(32), 0, st, ip, sp, n_items); }
+            } else if (ssim) PML_LAUNCH(identity_sweep_kernel<true>, g, dim3(32), 0, st, ip);
+            else             PML_LAUNCH(identity_sweep_kernel<false>, g, dim3(32), 0, st, ip);
         }
     } else if (pl.n_id > 0) {
         dim3 g((p->W + 255) / 256, p->H, p->B);
@@ -333,7 +343,7 @@ int run_loss(const pml_problem* p, void* ws, size_t ws_bytes, cudaStream_t st, b
         fq.smooth_blocks[i] = pl.smooth_blocks[i]; fq.smooth_off[i] = pl.smooth_off[i];
         fq.hd[i] = p->pass[i].hd; fq.wd[i] = p->pass[i].wd; fq.smooth_weight[i] = p->pass[i].smooth_weight;
     }
-    fq.losses = p->losses; fq.grad_T = p->grad_T; fq.grad_disp_const = p->grad_disp_const;
+    fq.losses = p->losses; fq.loss_vector = p->loss_vector; fq.grad_T = p->grad_T; fq.grad_disp_const = p->grad_disp_const;
     fq.image_part = imagepart;
     PML_LAUNCH(finalize_image_kernel, dim3(p->B, p->n_pass), dim3(256), 0, st, fq);
     PML_LAUNCH(finalize_loss_kernel, dim3(p->n_pass), dim3(32), 0, st, fq);
@@ -386,9 +396,13 @@ int pml_scale_grads(int32_t n_pass, int32_t B, int32_t S, const int32_t* hd, con
     }
     sp.off[n_pass] = total;
     sp.gconst = grad_disp_const; sp.gT = grad_T; sp.up = upstream; sp.gT_out = grad_T_out;
-    long long work = total + (long long)S * B * 16;
-    int blocks = (int)((work + 255) / 256);
-    PML_LAUNCH(pml::scale_grads_kernel, dim3(blocks), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), sp);
+    int max_n = 1;
+    for (int i = 0; i < n_pass; ++i) if (sp.per_image[i] > max_n) max_n = sp.per_image[i];
+    int chunks = (max_n + pml::kScaleChunk - 1) / pml::kScaleChunk;
+    const int pose_blocks = (S * B * 16 + 255) / 256;            // spread over the (x, y) extent of plane n_pass
+    while (chunks * B < pose_blocks) ++chunks;
+    if (B > 65535) return PML_ERR_UNSUPPORTED;
+    PML_LAUNCH(pml::scale_grads_kernel, dim3(chunks, B, n_pass + 1), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), sp);
     return cudaGetLastError() == cudaSuccess ? PML_OK : PML_ERR_CUDA;
 }
 

@@ -19,25 +19,39 @@ struct ScaleParams {
     float* gT_out;         // [S][B][16]
 };
 
+// grid = (chunks, B, n_pass + 1): planes z < n_pass scale one image of one scale (float4 where the
+// image size allows), plane z == n_pass reduces the pose gradients over the scales.
+constexpr int kScaleChunk = 256 * 4 * 4;   // elements per block: 256 threads x 4 float4
 __global__ void __launch_bounds__(256)
 scale_grads_kernel(const ScaleParams q) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = q.off[q.n_pass];
-    if (i < total) {
-        int pi = 0;
-#pragma unroll 1
-        for (int k = 1; k < q.n_pass; ++k) if (i >= q.off[k]) pi = k;
-        long long rel = i - q.off[pi];
-        int b = (int)(rel / q.per_image[pi]);
-        q.g[pi][rel] = q.up[pi] * (q.g[pi][rel] + q.gconst[pi * q.B + b]);
-    } else {
-        long long e = i - total;
-        if (e < (long long)q.S * q.B * 16) {
+    const int pi = blockIdx.z, b = blockIdx.y;
+    if (pi == q.n_pass) {
+        const int e = (blockIdx.y * gridDim.x + blockIdx.x) * 256 + threadIdx.x;
+        if (e < q.S * q.B * 16) {
             float acc = 0.f;
-            for (int pi = 0; pi < q.n_pass; ++pi)
-                acc = fmaf(q.up[pi], q.gT[(size_t)pi * q.S * q.B * 16 + e], acc);
+            for (int k = 0; k < q.n_pass; ++k)
+                acc = fmaf(q.up[k], q.gT[(size_t)k * q.S * q.B * 16 + e], acc);
             q.gT_out[e] = acc;
         }
+        return;
+    }
+    const int n = q.per_image[pi];
+    const int base = blockIdx.x * kScaleChunk;
+    if (base >= n) return;
+    const float up = __ldg(q.up + pi), c = __ldg(q.gconst + pi * q.B + b);
+    float* g = q.g[pi] + (size_t)b * n;
+    if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = base + (k * 256 + threadIdx.x) * 4;
+            if (i < n) {
+                float4 v = *reinterpret_cast<float4*>(g + i);
+                v.x = up * (v.x + c); v.y = up * (v.y + c); v.z = up * (v.z + c); v.w = up * (v.w + c);
+                *reinterpret_cast<float4*>(g + i) = v;
+            }
+        }
+    } else {
+        for (int i = base + threadIdx.x; i < min(base + kScaleChunk, n); i += 256) g[i] = up * (g[i] + c);
     }
 }
 

@@ -611,6 +611,7 @@ struct FinalizeParams {
     float smooth_weight[PML_MAX_PASSES];
     float* image_part;         // [n_pass][B][4]: photometric sum, smooth x sum, smooth y sum, -
     float* losses;             // [n_pass][4]
+    float* loss_vector;        // [n_pass] or null: loss_s once more, contiguous
     float* grad_T;             // [n_pass][S][B][16]
     float* grad_disp_const;    // [n_pass][B]
 };
@@ -681,6 +682,7 @@ finalize_loss_kernel(const FinalizeParams q) {
     q.losses[pi * 4 + 1] = photo;
     q.losses[pi * 4 + 2] = sm;
     q.losses[pi * 4 + 3] = 0.f;
+    if (q.loss_vector != nullptr) q.loss_vector[pi] = photo + q.smooth_weight[pi] * sm;
 }
 
 }  // namespace pml

@@ -52,12 +52,11 @@ struct IdentityParams {
     int TH, n_strips, n_chunks;
 };
 
-// grid = (n_chunks * n_strips, B), 32 threads
+// one warp = one (chunk, strip) item `bx` of image `b`
 template <bool SSIM>
-__global__ void __launch_bounds__(32)
-identity_sweep_kernel(const IdentityParams p) {
-    const int lane = threadIdx.x, b = blockIdx.y;
-    const int chunk = blockIdx.x / p.n_strips, strip = blockIdx.x - chunk * p.n_strips;
+__device__ __forceinline__ void identity_sweep_body(const IdentityParams& p, const int bx, const int b) {
+    const int lane = threadIdx.x;
+    const int chunk = bx / p.n_strips, strip = bx - chunk * p.n_strips;
     const int H = p.H, W = p.W, plane = H * W;
     const int x0 = strip * kPrepTW, x1 = min(x0 + kPrepTW, W);
     const int y0 = chunk * p.TH, y1 = min(y0 + p.TH, H);
@@ -146,6 +145,13 @@ identity_sweep_kernel(const IdentityParams p) {
     }
 }
 
+// grid = (n_chunks * n_strips, B), 32 threads
+template <bool SSIM>
+__global__ void __launch_bounds__(32)
+identity_sweep_kernel(const IdentityParams p) {
+    identity_sweep_body<SSIM>(p, blockIdx.x, blockIdx.y);
+}
+
 // ---------------------------------------------------------------------------------------------
 // smoothness term: grid = (sum over passes of B * strips_i * chunks_i), 32 threads.  Lane 0 and 31
 // are halo columns (they supply the left neighbour's right-edge term and the right neighbour's
@@ -157,14 +163,13 @@ constexpr int kSmoothTH = 32;   // rows per item
 __device__ __forceinline__ float sgn1(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }
 
 template <bool GRAD>
-__global__ void __launch_bounds__(32)
-smooth_sweep_kernel(const SmoothParams q) {
+__device__ __forceinline__ void smooth_sweep_body(const SmoothParams& q, const int item) {
     const int lane = threadIdx.x;
     int pi = 0;
 #pragma unroll 1
-    for (int i = 1; i < q.n_pass; ++i) if ((int)blockIdx.x >= q.pass[i].block_off) pi = i;
+    for (int i = 1; i < q.n_pass; ++i) if (item >= q.pass[i].block_off) pi = i;
     const SmoothPass& ps = q.pass[pi];
-    int rel = blockIdx.x - ps.block_off;
+    int rel = item - ps.block_off;
     const int b = rel / ps.blocks;
     rel -= b * ps.blocks;
     const int h = ps.h, w = ps.w, n = h * w;
@@ -178,7 +183,7 @@ smooth_sweep_kernel(const SmoothParams q) {
     const bool has_right = (cx >= 0) && (cx + 1 < w) && (lane < 31);   // edge (cx, cx+1) exists and is computable here
 
     const float mean = image_mean(q, pi, b);
-    if (blockIdx.x == (unsigned)(ps.block_off + b * ps.blocks) && lane == 0) q.disp_mean[pi * q.B + b] = mean;
+    if (item == ps.block_off + b * ps.blocks && lane == 0) q.disp_mean[pi * q.B + b] = mean;
     const float inv = __fdiv_rn(1.0f, mean + 1e-7f);
     const float nx_ = 1.0f / ((float)q.B * (float)h * (float)(w - 1));
     const float ny_ = 1.0f / ((float)q.B * (float)(h - 1) * (float)w);
@@ -245,8 +250,30 @@ smooth_sweep_kernel(const SmoothParams q) {
     }
     ex = warp_sum(ex); ey = warp_sum(ey); gd = warp_sum(gd);
     if (lane == 0) {
-        float* o = q.part + (size_t)blockIdx.x * 3;
+        float* o = q.part + (size_t)item * 3;
         o[0] = ex; o[1] = ey; o[2] = gd;
+    }
+}
+
+template <bool GRAD>
+__global__ void __launch_bounds__(32)
+smooth_sweep_kernel(const SmoothParams q) {
+    smooth_sweep_body<GRAD>(q, (int)blockIdx.x);
+}
+
+// Both preparation sweeps in ONE launch: the two are independent (identity losses read the images,
+// the smoothness term the disparities), each alone leaves the machine under-filled (0.7 waves of
+// latency-bound warps), together they overlap.  Identity items come first (they run longer).
+template <bool SSIM, bool GRAD>
+__global__ void __launch_bounds__(32)
+prep_kernel(const IdentityParams ip, const SmoothParams sp, const int n_identity_items) {
+    const int bx = (int)blockIdx.x;
+    if (bx < n_identity_items) {
+        const int per_image = ip.n_chunks * ip.n_strips;
+        const int b = bx / per_image;
+        identity_sweep_body<SSIM>(ip, bx - b * per_image, b);
+    } else {
+        smooth_sweep_body<GRAD>(sp, bx - n_identity_items);
     }
 }
 

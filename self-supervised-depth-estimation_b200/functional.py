@@ -128,7 +128,8 @@ class _PhotometricLoss(torch.autograd.Function):
                     ps.grad_frame_weight = gw.data_ptr()
                     gfws.append(gw)
         losses4 = torch.empty((n_pass, 4), **f32)
-        prob.losses = losses4.data_ptr()
+        loss = torch.empty((n_pass,), **f32)
+        prob.losses, prob.loss_vector = losses4.data_ptr(), loss.data_ptr()
         if want_grad:
             grad_T = torch.empty((n_pass, S, B, 4, 4), **f32)
             grad_const = torch.empty((n_pass, B), **f32)
@@ -153,7 +154,6 @@ class _PhotometricLoss(torch.autograd.Function):
             ctx.gdisps, ctx.grad_T, ctx.grad_const, ctx.gfws = gdisps, grad_T, grad_const, gfws
             ctx.shapes = [(d.shape[2], d.shape[3]) for d in disps]
             ctx.B, ctx.S, ctx.consumed = B, S, False
-        loss = losses4[:, 0].clone()
         outs = [loss, losses4] + argmins + [t for t in depths if t is not None] + [t for t in warpeds if t is not None]
         ctx.mark_non_differentiable(*outs[1:])
         ctx.layout = (n_pass, [t is not None for t in depths], [t is not None for t in warpeds])
