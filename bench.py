@@ -116,7 +116,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 def make_sets(args, n_sets, rank):
     from ssde_b200 import synthetic
-    srcs = [-1, 1, -2, 2][:args.sources]
+    srcs = [-1, 1, -2, 2, -3, 3, -4, 4][:args.sources]
     opt = synthetic.make_options(args.height, args.width, batch_size=args.batch)
     sets = []
     for i in range(n_sets):
@@ -342,7 +342,7 @@ def run_ours(args, rank, world, dev):
 def cpu_step_time(args, batch, reps, warm=1):
     from oracle import photometric_oracle as po
     from ssde_b200 import synthetic
-    srcs = [-1, 1, -2, 2][:args.sources]
+    srcs = [-1, 1, -2, 2, -3, 3, -4, 4][:args.sources]
     opt = synthetic.make_options(args.height, args.width, batch_size=batch)
     inputs, outputs = synthetic.make_batch(batch, args.height, args.width, sources=srcs, seed=0)
     times = []

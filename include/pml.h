@@ -30,8 +30,8 @@
 extern "C" {
 #endif
 
-#define PML_ABI_VERSION 2
-#define PML_MAX_SOURCES 4 /* source frames per target, e.g. (-1, 1, "s") = 3 */
+#define PML_ABI_VERSION 3
+#define PML_MAX_SOURCES 8 /* source frames per target, e.g. (-1, 1, "s") = 3; BASELINE config 5 sweeps 2/4/8 */
 #define PML_MAX_PASSES 8  /* scales handled by one call */
 
 typedef struct CUstream_st* pml_stream_t; /* == cudaStream_t */

@@ -8,8 +8,8 @@ import os
 from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t,
                     c_uint32, c_uint64, c_void_p)
 
-PML_ABI_VERSION = 2
-PML_MAX_SOURCES = 4
+PML_ABI_VERSION = 3
+PML_MAX_SOURCES = 8
 PML_MAX_PASSES = 8
 PML_FLAG_NO_SSIM = 1
 PML_FLAG_NO_AUTOMASK = 2

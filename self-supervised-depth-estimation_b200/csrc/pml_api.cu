@@ -76,6 +76,7 @@ int validate(const pml_problem* p, bool grad) {
 bool use_sweep(const pml_problem* p) {
     if (p->pass[0].frame_weight) return true;   // predictive mask: pair sweeps around select_kernel
     const char* k = getenv("PML_KERNEL");
+    if (p->S > 4) return true;                  // the CTA-strip kernel is instantiated for S <= 4
     if (k && k[0] == 'c') return false;
     if (k && k[0] == 's') return true;
     return p->S != 3;

@@ -619,23 +619,23 @@ struct FinalizeParams {
 __global__ void __launch_bounds__(256)
 finalize_image_kernel(const FinalizeParams q) {
     __shared__ float s_col[1 + 12 * PML_MAX_SOURCES];
-    __shared__ float s_seg[4][64];
+    __shared__ float s_seg[2][128];
     __shared__ float s_w[8][3];
     const int tid = threadIdx.x, b = blockIdx.x, pi = blockIdx.y;
     const int ncol = q.with_grad ? 1 + 12 * q.S : 1;
-    // photometric partial columns of this image's work items: four interleaved segments per column,
-    // each summed in item order, then combined in segment order (fixed order => deterministic)
+    // photometric partial columns of this image's work items (up to 1 + 12 * 8 = 97): two interleaved
+    // segments per column, each summed in item order, then combined (fixed order => deterministic)
     {
-        const int col = tid & 63, seg = tid >> 6;
+        const int col = tid & 127, seg = tid >> 7;
         float v = 0.f;
         if (col < ncol) {
             const float* base = q.part + (size_t)(pi * q.cta_per_pass + b * q.cta_per_image) * q.part_stride + col;
-            for (int c = seg; c < q.cta_per_image; c += 4) v += base[(size_t)c * q.part_stride];
+            for (int c = seg; c < q.cta_per_image; c += 2) v += base[(size_t)c * q.part_stride];
         }
         s_seg[seg][col] = v;
     }
     __syncthreads();
-    if (tid < ncol) s_col[tid] = (s_seg[0][tid] + s_seg[1][tid]) + (s_seg[2][tid] + s_seg[3][tid]);
+    if (tid < ncol) s_col[tid] = s_seg[0][tid] + s_seg[1][tid];
     // smoothness partials of this image
     const int nb = q.smooth_blocks[pi];
     const float* sp = q.smooth_part + ((size_t)q.smooth_off[pi] + (size_t)b * nb) * 3;

@@ -666,10 +666,12 @@ select_kernel(const PhotoParams p) {
             float best = 3.0e38f;
             int best_i = 0;
             if (n_id > 0) {
-                float nz[4] = {0.f, 0.f, 0.f, 0.f};
-                if (nz_b == nullptr) {
-                    philox2_normal2(key, (uint32_t)(b * plane + pix), (uint32_t)pass_i, nz[0], nz[1]);
-                    if (n_id > 2) philox2_normal2(key, (uint32_t)(b * plane + pix), (uint32_t)pass_i + 0x10000u, nz[2], nz[3]);
+                float nz[PML_MAX_SOURCES];
+#pragma unroll
+                for (int i = 0; i < PML_MAX_SOURCES; i += 2) {
+                    nz[i] = nz[i + 1] = 0.f;
+                    if (nz_b == nullptr && i < n_id)
+                        philox2_normal2(key, (uint32_t)(b * plane + pix), (uint32_t)pass_i + 0x10000u * (uint32_t)(i >> 1), nz[i], nz[i + 1]);
                 }
 #pragma unroll
                 for (int i = 0; i < PML_MAX_SOURCES; ++i) {

@@ -74,9 +74,16 @@ def check(got, opt, variant, inputs, outputs, seed, ref32=None, ref64=None, sour
     rep = report if report is not None else {}
     n_id = 0 if opt.disable_automasking else (1 if opt.avg_reprojection else len(sources))
     # ---- losses
+    # fp32 floor of the total: the per-scale deviations of the fp32 reference can cancel in its own
+    # total by luck (min over many frames -> tiny losses dominated by SSIM's variance cancellation),
+    # so the total is judged against the magnitude-weighted per-scale floors as well
+    floor_total = sum(abs(float(ref32["loss/%d" % s]) - float(ref64["loss/%d" % s])) for s in opt.scales) / \
+        max(sum(abs(float(ref64["loss/%d" % s])) for s in opt.scales), 1e-30)
     for k in ["loss"] + ["loss/%d" % s for s in opt.scales]:
         e = common.rel_err(got[k], ref64[k])
         floor = common.rel_err(ref32[k], ref64[k])
+        if k == "loss":
+            floor = max(floor, floor_total)
         rep[k] = e
         assert e <= LOSS_TOL + 2 * floor, "%s: rel err %.3e (fp32 reference itself %.3e)" % (k, e, floor)
     # ---- selection
@@ -89,7 +96,12 @@ def check(got, opt, variant, inputs, outputs, seed, ref32=None, ref64=None, sour
             n, n_far = common.argmin_report(a, ref64.get("argmin/%d" % s, o64["argmin/%d" % s]), o64["margin/%d" % s], eps=TIE_EPS)
             rep["argmin/%d" % s] = (n, n_far)
             assert n_far == 0, "scale %d: %d selection mismatches beyond near-ties" % (s, n_far)
-            assert n <= max(4, a.numel() // 200), "scale %d: %d near-tie flips of %d" % (s, n, a.numel())
+            # ... and rare: at most 0.5 % of the pixels, or twice what the fp32 reference itself flips
+            # against its float64 run (many candidates with tiny losses sit inside fp32 round-off)
+            n_ref = 0
+            if "argmin/%d" % s in ref32 and "argmin/%d" % s in ref64:
+                n_ref = int((ref32["argmin/%d" % s].long() != ref64["argmin/%d" % s].long()).sum())
+            assert n <= max(4, a.numel() // 200, 2 * n_ref), "scale %d: %d near-tie flips of %d (fp32 reference: %d)" % (s, n, a.numel(), n_ref)
         k = "identity_selection/%d" % s
         if k in got:
             assert torch.equal(got[k], (a.long() > n_id - 1).float()), k

@@ -45,6 +45,7 @@ def test_three_sources_with_stereo(emu_lib):
 
 
 @pytest.mark.parametrize("sources,over", [((-1, 1, -2, 2), {}), ((-1, 1, "s"), dict(avg_reprojection=True)),
+                                          ((-1, 1, -2, 2, -3, 3, -4, 4), {}), ((-1, 1, -2, 2, "s"), {}),
                                           ((-1, 1, -2), dict(disable_automasking=True)), ((-1, 1, -2, 2), dict(no_ssim=True))])
 def test_more_than_two_sources_pair_sweeps(emu_lib, sources, over, monkeypatch):
     # S > 2: forward sweep per frame pair -> select_kernel -> forward+adjoint sweep per pair
@@ -91,8 +92,8 @@ def test_host_rejects_bad_inputs(emu_lib):
     kw = dict(smooth_weights=[1e-3])
     with pytest.raises(TypeError):      # fp64 is not silently converted
         functional.photometric_loss(tgt.double(), srcs, K, iK, Ts, [outputs[("disp", 0)]], [tgt], **kw)
-    with pytest.raises(ValueError):     # 5 sources > PML_MAX_SOURCES
-        functional.photometric_loss(tgt, srcs * 3, K, iK, Ts * 3, [outputs[("disp", 0)]], [tgt], **kw)
+    with pytest.raises(ValueError):     # 10 sources > PML_MAX_SOURCES
+        functional.photometric_loss(tgt, srcs * 5, K, iK, Ts * 5, [outputs[("disp", 0)]], [tgt], **kw)
     with pytest.raises(ValueError):     # smoothness colour must match the disparity resolution
         functional.photometric_loss(tgt, srcs, K, iK, Ts, [outputs[("disp", 1)]], [tgt], **kw)
     with pytest.raises(_cabi.PmlError):  # 3:1 ratio is not a power of two

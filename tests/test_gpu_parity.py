@@ -25,6 +25,7 @@ CONFIGS = {
     "c4_gru_seq5": dict(B=5, H=192, W=640, sources=(-1, 1), variant="gru", style="kitti", len_sequence=5),
     "c5_small_96x320_s1": dict(B=3, H=96, W=320, sources=(1,), variant="trainer", style="kitti"),
     "c5_s4": dict(B=1, H=96, W=320, sources=(-1, 1, -2, 2), variant="trainer", style="kitti"),
+    "c5_s8": dict(B=1, H=96, W=320, sources=(-1, 1, -2, 2, -3, 3, -4, 4), variant="trainer", style="kitti"),
     "uniform_stress": dict(B=2, H=96, W=320, sources=(-1, 1), variant="trainer", style="uniform"),
     "out_of_frustum": dict(B=2, H=96, W=320, sources=(-1, 1), variant="trainer", style="oof"),
     "tanh_range_disp": dict(B=2, H=64, W=160, sources=(-1, 1), variant="fusion", style="kitti", neg_disp=True),
