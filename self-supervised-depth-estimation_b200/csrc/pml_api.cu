@@ -26,6 +26,7 @@ struct Plan {
     bool sweep;   // warp-strip kernel (pml_sweep.cuh) instead of the CTA-strip kernel
     bool two_sweeps;   // S > 2 or predictive mask: forward sweep per frame pair, selection, adjoint sweep
     int NT, TW, TH, n_strips, n_chunks, cta_per_pass, n_cta, part_stride;
+    int TH_fwd, n_chunks_fwd;   // chunk geometry of forward-only sweeps that write no partials
     int n_id;
     int smooth_blocks[PML_MAX_PASSES], smooth_off[PML_MAX_PASSES], smooth_total;
     int max_chunks;
@@ -69,17 +70,18 @@ int validate(const pml_problem* p, bool grad) {
 }
 
 // Which fused kernel serves this problem.  The warp-strip sweep (pml_sweep.cuh) packs two source
-// frames of a pixel into fp32x2 values; four frames are swept pair by pair around a selection
-// kernel (2.0 ms vs 4.1 ms for the CTA-strip kernel at the headline size).  Three frames would leave
-// half of the second pair idle -- there the first-generation CTA-strip kernel (templated on S) is
-// still ahead (3.0 vs 3.4 ms at B=8, 320x1024) and is kept.  PML_KERNEL=cta / sweep force a choice.
+// frames of a pixel into fp32x2 values; more frames are swept pair by pair (forward sweeps of all
+// pairs but the last, the last pair's sweep selects over everything and carries its adjoint, then
+// the adjoint sweeps of the others).  It is ahead of the first-generation CTA-strip kernel
+// (pml_photometric.cuh, templated on S <= 4) everywhere -- S=3 at B=8, 320x1024: 2.5 vs 2.8 ms;
+// S=4 at the headline size: 1.4 vs 3.9 ms -- which is kept as an independent implementation for the
+// cross-check test.  PML_KERNEL=cta forces it.
 bool use_sweep(const pml_problem* p) {
     if (p->pass[0].frame_weight) return true;   // predictive mask: pair sweeps around select_kernel
     const char* k = getenv("PML_KERNEL");
     if (p->S > 4) return true;                  // the CTA-strip kernel is instantiated for S <= 4
     if (k && k[0] == 'c') return false;
-    if (k && k[0] == 's') return true;
-    return p->S != 3;
+    return true;
 }
 
 Plan make_plan(const pml_problem* p, bool grad) {
@@ -105,17 +107,30 @@ Plan make_plan(const pml_problem* p, bool grad) {
     // strip height: the tallest chunk that still yields ~6 CTAs per SM (4 halo rows per chunk);
     // warp strips: ~1.5-2 waves of the 8 warps an SM holds (5 halo row steps per chunk; measured on
     // B200 at the headline size: TH 96 beats 48 and 32)
+    // The forward-only instantiations need fewer registers (12 resident warps per SM instead of 8) and
+    // get their own, shorter chunks; the launches of one call that write no partials (sweep mode 1) use
+    // the forward geometry even inside a forward+backward call.
     int per_chunk = p->n_pass * p->B * pl.n_strips;
-    int want = ((pl.sweep ? kNumSM * 12 : kNumSM * 6) + per_chunk - 1) / per_chunk;
-    if (want < 1) want = 1;
-    int th = (p->H + want - 1) / want;
-    if (th < 16) th = 16;
-    th = ((th + 7) / 8) * 8;
-    th = env_int("PML_TH", th);
-    if (th > p->H) th = p->H;
-    if (th < 4) th = 4;
-    pl.TH = th;
+    auto chunk_rows = [&](int target_items) {
+        int want = (target_items + per_chunk - 1) / per_chunk;
+        if (want < 1) want = 1;
+        int th = (p->H + want - 1) / want;
+        if (th < 16) th = 16;
+        th = ((th + 7) / 8) * 8;
+        th = env_int("PML_TH", th);
+        if (th > p->H) th = p->H;
+        if (th < 4) th = 4;
+        return th;
+    };
+    // ~1.5 work items per resident-warp slot: 8 warps/SM for the forward+backward sweeps (255 registers),
+    // 12 for the generic forward-only one (168), 16 for the forward-only default configuration (128)
+    bool common_fwd = p->S == 2 && !(p->flags & (PML_FLAG_NO_AUTOMASK | PML_FLAG_AVG_REPROJ));
+    for (int i = 0; i < p->n_pass; ++i)
+        common_fwd = common_fwd && !p->pass[i].noise && !p->pass[i].depth && !p->pass[i].warped && !p->pass[i].frame_weight;
+    pl.TH_fwd = pl.sweep ? chunk_rows(kNumSM * (common_fwd ? 24 : 18)) : chunk_rows(kNumSM * 6);
+    pl.TH = (pl.sweep && !grad) ? pl.TH_fwd : chunk_rows(pl.sweep ? kNumSM * 12 : kNumSM * 6);
     pl.n_chunks = (p->H + pl.TH - 1) / pl.TH;
+    pl.n_chunks_fwd = (p->H + pl.TH_fwd - 1) / pl.TH_fwd;
     pl.cta_per_pass = p->B * pl.n_chunks * pl.n_strips;
     pl.n_cta = pl.cta_per_pass * p->n_pass;
     pl.part_stride = ((1 + 12 * p->S) + 3) & ~3;
@@ -150,7 +165,6 @@ Plan make_plan(const pml_problem* p, bool grad) {
         off = align16(off + (size_t)p->n_pass * p->B * p->H * p->W);
     }
     pl.total = off;
-    (void)grad;
     return pl;
 }
 
@@ -187,7 +201,10 @@ int launch_sweep(const PhotoParams& pp, cudaStream_t st) {
     } else if (pp.mode == 0) {
         if (emit) PML_LAUNCH((sweep_kernel<GRAD, SSIM, 0, true>), grid, blk, smem, st, pp);
         else      PML_LAUNCH((sweep_kernel<GRAD, SSIM, 0, false>), grid, blk, smem, st, pp);
-    } else if (!GRAD) {
+    } else if (pp.mode == 3) {
+        if (emit) PML_LAUNCH((sweep_kernel<GRAD, SSIM, 3, true>), grid, blk, smem, st, pp);
+        else      PML_LAUNCH((sweep_kernel<GRAD, SSIM, 3, false>), grid, blk, smem, st, pp);
+    } else if (pp.mode == 1) {
         if (emit) PML_LAUNCH((sweep_kernel<false, SSIM, 1, true>), grid, blk, smem, st, pp);
         else      PML_LAUNCH((sweep_kernel<false, SSIM, 1, false>), grid, blk, smem, st, pp);
     } else {
@@ -312,16 +329,23 @@ int run_loss(const pml_problem* p, void* ws, size_t ws_bytes, cudaStream_t st, b
         for (int i = 0; i < p->n_pass; ++i)
             if (!pp.pass[i].argmin)
                 pp.pass[i].argmin = reinterpret_cast<uint8_t*>(base + pl.off_argmin) + (size_t)i * p->B * p->H * p->W;
-        pp.mode = 1;
-        for (int fa = 0; fa < p->S && rc == PML_OK; fa += 2) {
-            pp.f_base = fa; pp.pair_n = (fa + 1 < p->S) ? 2 : 1;
+        // forward sweeps of all pairs but the last (reprojection losses -> rp); the last pair's sweep
+        // selects over everything and carries its own adjoint; then the adjoint sweeps of the others
+        const int last_fa = ((p->S - 1) / 2) * 2;
+        pp.mode = 1; pp.TH = pl.TH_fwd; pp.n_chunks = pl.n_chunks_fwd;
+        for (int fa = 0; fa < last_fa && rc == PML_OK; fa += 2) {
+            pp.f_base = fa; pp.pair_n = 2;
             rc = ssim ? launch_sweep<false, true>(pp, st) : launch_sweep<false, false>(pp, st);
         }
-        if (rc == PML_OK)
-            PML_LAUNCH(select_kernel, dim3(pp.n_chunks * pp.n_strips, pp.B, pp.n_pass), dim3(32), 0, st, pp);
+        pp.TH = pl.TH; pp.n_chunks = pl.n_chunks;
+        if (rc == PML_OK) {
+            pp.mode = 3; pp.f_base = last_fa; pp.pair_n = (last_fa + 1 < p->S) ? 2 : 1;
+            if (grad) rc = ssim ? launch_sweep<true, true>(pp, st) : launch_sweep<true, false>(pp, st);
+            else      rc = ssim ? launch_sweep<false, true>(pp, st) : launch_sweep<false, false>(pp, st);
+        }
         pp.mode = 2;
-        for (int fa = 0; grad && fa < p->S && rc == PML_OK; fa += 2) {
-            pp.f_base = fa; pp.pair_n = (fa + 1 < p->S) ? 2 : 1;
+        for (int fa = 0; grad && fa < last_fa && rc == PML_OK; fa += 2) {
+            pp.f_base = fa; pp.pair_n = 2;
             rc = ssim ? launch_sweep<true, true>(pp, st) : launch_sweep<true, false>(pp, st);
         }
     } else if (pl.sweep) {
@@ -370,7 +394,8 @@ const char* pml_strerror(int status) {
 
 size_t pml_workspace_bytes(const pml_problem* p) {
     if (validate(p, false) != PML_OK) return 0;
-    return make_plan(p, true).total;
+    const size_t a = make_plan(p, true).total, b = make_plan(p, false).total;   // either call may follow
+    return a > b ? a : b;
 }
 
 int pml_loss_forward(const pml_problem* p, void* ws, size_t ws_bytes, pml_stream_t stream) {

@@ -138,7 +138,9 @@ __device__ __noinline__ void sweep_flush_row(float* sG, float* gd_row, float h, 
     __syncwarp();
 }
 
-// MODE (see PhotoParams::mode): 0 selection in the sweep; 1 reprojection losses only; 2 selection given.
+// MODE (see PhotoParams::mode): 0 selection in the sweep (all frames in this pair); 1 reprojection losses
+// only (stored); 2 selection given (adjoint of an earlier pair); 3 last pair of several: selection over the
+// identity candidates, the stored losses of the earlier pairs and this pair, per-frame weights applied.
 // EMIT: some pass wants the by-products outputs[("depth",0,s)] / outputs[("color",f,s)] (trainer.py:480,
 // :508) written.  The hot loop is two unrolled row steps of ~1000 instructions; keeping it under the 32 KB
 // instruction cache matters (measured: 0.408 -> 0.371 ms), so everything optional is compiled out.
@@ -562,6 +564,66 @@ sweep_kernel(const PhotoParams p) {
                     wgt = mul2(wgt, f2(__ldg(mq), two ? __ldg(at(mq, plane)) : 0.f));
                 }
             }
+        } else if (mode == 3) {
+            if (p_valid) {
+                const int pix = py * W + cx;
+                float best = 3.0e38f;
+                int best_i = 0;
+                // identity candidates + tie-break noise (trainer.py:592-597), any number of them
+                for (int i = 0; i < n_sel; i += 2) {
+                    float n0 = 0.f, n1 = 0.f;
+                    const int o = (b * n_sel + i) * plane + pix;
+                    if (ps.noise != nullptr) {
+                        n0 = __ldg(at(ps.noise, o));
+                        if (i + 1 < n_sel) n1 = __ldg(at(ps.noise, o + plane));
+                    } else {
+                        philox2_normal2((uint32_t)p.seed ^ ((uint32_t)(p.seed >> 32) * 0x9E3779B9u), (uint32_t)(bp + pix),
+                                        (uint32_t)pass_i + 0x10000u * (uint32_t)(i >> 1), n0, n1);
+                    }
+                    const float c0 = fmaf(n0, kTieNoise, __ldg(at(id_g, o)));
+                    if (c0 < best) { best = c0; best_i = i; }
+                    if (i + 1 < n_sel) {
+                        const float c1 = fmaf(n1, kTieNoise, __ldg(at(id_g, o + plane)));
+                        if (c1 < best) { best = c1; best_i = i + 1; }
+                    }
+                }
+                // reprojection losses of the pairs swept before (mode 1), in frame order, then this pair;
+                // the predictive mask weighs every frame (trainer.py:579)
+                const float* rq = p.rp + ((size_t)(pass_i * S) * p.B + b) * plane + pix;   // frame stride: B * plane
+                const float* mq = (ps.fw != nullptr) ? at(ps.fw, b * S * plane + pix) : nullptr;
+                float rsum = 0.f;
+                for (int f = 0; f < fa; ++f) {
+                    float r = __ldg(at(rq, f * p.B * plane));
+                    if (mq != nullptr) r *= __ldg(at(mq, f * plane));
+                    if (avg) rsum += r;
+                    else if (r < best) { best = r; best_i = n_sel + f; }
+                }
+                const float2 m = (mq != nullptr) ? f2(__ldg(at(mq, fa * plane)), two ? __ldg(at(mq, fb * plane)) : 0.f) : splat(1.f);
+                const float2 rw = mul2(rp, m);
+                if (avg) {
+                    const float mean = (rsum + rw.x + (two ? rw.y : 0.f)) / (float)S;     // trainer.py:585-586
+                    if (mean < best) { best = mean; best_i = n_sel; }
+                    wgt = (best_i == n_sel) ? f2(1.0f / (float)S, two ? 1.0f / (float)S : 0.f) : splat(0.f);
+                } else {
+                    if (rw.x < best) { best = rw.x; best_i = n_sel + fa; }
+                    if (two && rw.y < best) { best = rw.y; best_i = n_sel + fb; }
+                    wgt = f2(best_i == n_sel + fa ? 1.f : 0.f, (two && best_i == n_sel + fb) ? 1.f : 0.f);
+                }
+                if (col_owned && py >= y0 && py < y1) {
+                    loss_acc += best;
+                    if (ps.argmin != nullptr) ps.argmin[bp + pix] = (uint8_t)best_i;
+                    if (ps.gfw != nullptr) {   // d mean(to_optimise) / d mask_f = [f selected] * rp_f / N
+                        float* gq = at(ps.gfw, b * S * plane + pix);
+                        for (int f = 0; f < fa; ++f) {
+                            const float sel = avg ? (best_i == n_sel ? 1.0f / (float)S : 0.f) : (best_i == n_sel + f ? 1.f : 0.f);
+                            *at(gq, f * plane) = sel * __ldg(at(rq, f * p.B * plane)) * p.inv_n;
+                        }
+                        *at(gq, fa * plane) = wgt.x * rp.x * p.inv_n;
+                        if (two) *at(gq, fb * plane) = wgt.y * rp.y * p.inv_n;
+                    }
+                }
+                wgt = mul2(wgt, m);     // d (rp * m) / d rp
+            }
         } else if (p_valid) {
             // candidates in the reference's order: identity (+noise) first, then reprojection
             // (trainer.py:597); torch.min returns the first minimum.
@@ -623,7 +685,7 @@ sweep_kernel(const PhotoParams p) {
     float* out = p.part + (size_t)item * p.part_stride;
     {
         const float v = warp_sum(loss_acc);
-        if (lane == 0 && mode == 0) out[0] = v;
+        if (lane == 0 && (mode == 0 || mode == 3)) out[0] = v;
     }
     if (GRAD) {
 #pragma unroll
@@ -635,85 +697,6 @@ sweep_kernel(const PhotoParams p) {
             }
         }
     }
-}
-
-// More than two source frames: per-pixel minimum over the identity candidates (+ tie-break noise)
-// and the reprojection losses of ALL frames (trainer.py:592-610), between the two sweeps.  Same work
-// items as the sweep (one warp per strip item) so that the loss partial lands in the item's row.
-__global__ void __launch_bounds__(32)
-select_kernel(const PhotoParams p) {
-    const int lane = threadIdx.x, b = blockIdx.y, pass_i = blockIdx.z;
-    const int chunk = blockIdx.x / p.n_strips, strip = blockIdx.x - chunk * p.n_strips;
-    const int item = (pass_i * p.B + b) * (p.n_chunks * p.n_strips) + blockIdx.x;
-    const PassDev& ps = p.pass[pass_i];
-    const int H = p.H, W = p.W, S = p.S, plane = H * W;
-    const int x0 = strip * kSweepTW, x1 = min(x0 + kSweepTW, W);
-    const int y0 = chunk * p.TH, y1 = min(y0 + p.TH, H);
-    const int cx = x0 + lane;
-    const bool automask = !(p.flags & PML_FLAG_NO_AUTOMASK);
-    const bool avg = (p.flags & PML_FLAG_AVG_REPROJ) != 0;
-    const int n_id = automask ? (avg ? 1 : S) : 0;
-    const float* id_b = p.identity + (size_t)b * n_id * plane;
-    const float* nz_b = (ps.noise != nullptr) ? ps.noise + (size_t)b * n_id * plane : nullptr;
-    const float* rp_b = p.rp + ((size_t)pass_i * S * p.B + b) * plane;     // frame stride: B * plane
-    const float* fw_b = (ps.fw != nullptr) ? ps.fw + (size_t)b * S * plane : nullptr;   // predictive mask
-    float* gfw_b = (ps.gfw != nullptr) ? ps.gfw + (size_t)b * S * plane : nullptr;
-    const uint32_t key = (uint32_t)p.seed ^ ((uint32_t)(p.seed >> 32) * 0x9E3779B9u);
-    float loss_acc = 0.f;
-    if (lane < kSweepTW && cx < x1) {
-        for (int y = y0; y < y1; ++y) {
-            const int pix = y * W + cx;
-            float best = 3.0e38f;
-            int best_i = 0;
-            if (n_id > 0) {
-                float nz[PML_MAX_SOURCES];
-#pragma unroll
-                for (int i = 0; i < PML_MAX_SOURCES; i += 2) {
-                    nz[i] = nz[i + 1] = 0.f;
-                    if (nz_b == nullptr && i < n_id)
-                        philox2_normal2(key, (uint32_t)(b * plane + pix), (uint32_t)pass_i + 0x10000u * (uint32_t)(i >> 1), nz[i], nz[i + 1]);
-                }
-#pragma unroll
-                for (int i = 0; i < PML_MAX_SOURCES; ++i) {
-                    if (i < n_id) {
-                        const float nv = (nz_b != nullptr) ? __ldg(nz_b + (size_t)i * plane + pix) : nz[i];
-                        const float cand = fmaf(nv, kTieNoise, __ldg(id_b + (size_t)i * plane + pix));
-                        if (cand < best) { best = cand; best_i = i; }
-                    }
-                }
-            }
-            float rsum = 0.f;
-            float rraw[PML_MAX_SOURCES];
-#pragma unroll
-            for (int f = 0; f < PML_MAX_SOURCES; ++f) {
-                rraw[f] = 0.f;
-                if (f < S) {
-                    float r = __ldg(rp_b + (size_t)f * p.B * plane + pix);
-                    rraw[f] = r;
-                    if (fw_b != nullptr) r *= __ldg(fw_b + (size_t)f * plane + pix);   // trainer.py:579
-                    if (avg) rsum += r;
-                    else if (r < best) { best = r; best_i = n_id + f; }
-                }
-            }
-            if (avg) {
-                const float m = rsum / (float)S;      // trainer.py:585-586
-                if (m < best) { best = m; best_i = n_id; }
-            }
-            loss_acc += best;
-            ps.argmin[(size_t)b * plane + pix] = (uint8_t)best_i;
-            if (gfw_b != nullptr) {   // d mean(to_optimise) / d mask_f = [f selected] * rp_f / N
-#pragma unroll
-                for (int f = 0; f < PML_MAX_SOURCES; ++f) {
-                    if (f < S) {
-                        const float sel = avg ? (best_i == n_id ? 1.0f / (float)S : 0.f) : (best_i == n_id + f ? 1.f : 0.f);
-                        gfw_b[(size_t)f * plane + pix] = sel * rraw[f] * p.inv_n;
-                    }
-                }
-            }
-        }
-    }
-    const float v = warp_sum(loss_acc);
-    if (lane == 0) p.part[(size_t)item * p.part_stride] = v;
 }
 
 inline size_t sweep_smem_bytes() { return (size_t)kSweepWarps * kSweepWarpFloats * sizeof(float) + 16; }

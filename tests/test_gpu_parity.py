@@ -93,7 +93,9 @@ def test_full_size_determinism_and_forward_only(cuda_lib):
     for s in opt.scales:
         assert torch.equal(a["argmin/%d" % s], b["argmin/%d" % s])
         assert torch.equal(a["argmin/%d" % s], c["argmin/%d" % s])
-        assert a["loss/%d" % s].item() == b["loss/%d" % s].item() == c["loss/%d" % s].item()
+        assert a["loss/%d" % s].item() == b["loss/%d" % s].item()
+        # the forward-only call uses shorter row chunks (more resident warps): same pixels, another summation order
+        assert abs(c["loss/%d" % s].item() - a["loss/%d" % s].item()) <= 1e-6 * abs(a["loss/%d" % s].item())
         assert torch.equal(a["grad_disp/%d" % s], b["grad_disp/%d" % s]) or \
             common.rel_err(a["grad_disp/%d" % s], b["grad_disp/%d" % s]) < 1e-6   # 4-way corner atomics
     assert torch.equal(a["grad_T/1"], b["grad_T/1"])
