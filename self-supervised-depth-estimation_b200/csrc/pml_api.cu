@@ -194,21 +194,25 @@ int launch_sweep(const PhotoParams& pp, cudaStream_t st) {
     bool emit = false;   // by-products requested by any pass (never in sweep mode 2)
     for (int i = 0; i < pp.n_pass; ++i) emit = emit || pp.pass[i].depth != nullptr || pp.pass[i].warped != nullptr;
     const dim3 blk(kSweepWarps * 32);
-    bool common = pp.mode == 0 && !emit && pp.S == 2 && !(pp.flags & (PML_FLAG_NO_AUTOMASK | PML_FLAG_AVG_REPROJ));
-    for (int i = 0; i < pp.n_pass; ++i) common = common && pp.pass[i].noise == nullptr;
-    if (common) {
-        PML_LAUNCH((sweep_kernel<GRAD, SSIM, 0, false, true>), grid, blk, smem, st, pp);
-    } else if (pp.mode == 0) {
-        if (emit) PML_LAUNCH((sweep_kernel<GRAD, SSIM, 0, true>), grid, blk, smem, st, pp);
-        else      PML_LAUNCH((sweep_kernel<GRAD, SSIM, 0, false>), grid, blk, smem, st, pp);
+    if (pp.mode == 2) emit = false;   // the adjoint sweeps of earlier pairs never write by-products
+    bool common = !emit && pp.pair_n == 2 && (pp.mode != 0 || pp.S == 2) &&
+                  !(pp.flags & (PML_FLAG_NO_AUTOMASK | PML_FLAG_AVG_REPROJ));
+    for (int i = 0; i < pp.n_pass; ++i) common = common && pp.pass[i].noise == nullptr && pp.pass[i].fw == nullptr;
+    if (pp.mode == 0) {
+        if (common)    PML_LAUNCH((sweep_kernel<GRAD, SSIM, 0, false, true>), grid, blk, smem, st, pp);
+        else if (emit) PML_LAUNCH((sweep_kernel<GRAD, SSIM, 0, true>), grid, blk, smem, st, pp);
+        else           PML_LAUNCH((sweep_kernel<GRAD, SSIM, 0, false>), grid, blk, smem, st, pp);
     } else if (pp.mode == 3) {
-        if (emit) PML_LAUNCH((sweep_kernel<GRAD, SSIM, 3, true>), grid, blk, smem, st, pp);
-        else      PML_LAUNCH((sweep_kernel<GRAD, SSIM, 3, false>), grid, blk, smem, st, pp);
+        if (common)    PML_LAUNCH((sweep_kernel<GRAD, SSIM, 3, false, true>), grid, blk, smem, st, pp);
+        else if (emit) PML_LAUNCH((sweep_kernel<GRAD, SSIM, 3, true>), grid, blk, smem, st, pp);
+        else           PML_LAUNCH((sweep_kernel<GRAD, SSIM, 3, false>), grid, blk, smem, st, pp);
     } else if (pp.mode == 1) {
-        if (emit) PML_LAUNCH((sweep_kernel<false, SSIM, 1, true>), grid, blk, smem, st, pp);
-        else      PML_LAUNCH((sweep_kernel<false, SSIM, 1, false>), grid, blk, smem, st, pp);
+        if (common)    PML_LAUNCH((sweep_kernel<false, SSIM, 1, false, true>), grid, blk, smem, st, pp);
+        else if (emit) PML_LAUNCH((sweep_kernel<false, SSIM, 1, true>), grid, blk, smem, st, pp);
+        else           PML_LAUNCH((sweep_kernel<false, SSIM, 1, false>), grid, blk, smem, st, pp);
     } else {
-        PML_LAUNCH((sweep_kernel<true, SSIM, 2, false>), grid, blk, smem, st, pp);
+        if (common)    PML_LAUNCH((sweep_kernel<true, SSIM, 2, false, true>), grid, blk, smem, st, pp);
+        else           PML_LAUNCH((sweep_kernel<true, SSIM, 2, false>), grid, blk, smem, st, pp);
     }
     return PML_OK;
 }

@@ -144,8 +144,9 @@ __device__ __noinline__ void sweep_flush_row(float* sG, float* gd_row, float h, 
 // EMIT: some pass wants the by-products outputs[("depth",0,s)] / outputs[("color",f,s)] (trainer.py:480,
 // :508) written.  The hot loop is two unrolled row steps of ~1000 instructions; keeping it under the 32 KB
 // instruction cache matters (measured: 0.408 -> 0.371 ms), so everything optional is compiled out.
-// COMMON: the default training configuration (two source frames, automask, per-frame min, in-kernel
-// tie-break noise) with its run-time flags folded into constants; the generic instantiation serves the rest.
+// COMMON: the default training configuration (a full pair of source frames, automask, per-frame min,
+// in-kernel tie-break noise, no predictive mask) with its run-time flags folded into constants; the
+// generic instantiation serves the rest.
 template <bool GRAD, bool SSIM, int MODE, bool EMIT, bool COMMON = false>
 __global__ void __launch_bounds__(kSweepWarps * 32)
 sweep_kernel(const PhotoParams p) {
@@ -171,9 +172,9 @@ sweep_kernel(const PhotoParams p) {
     const bool automask = COMMON ? true : !(p.flags & PML_FLAG_NO_AUTOMASK);
     const bool avg = COMMON ? false : (p.flags & PML_FLAG_AVG_REPROJ) != 0;
     constexpr int mode = MODE;
-    const int n_sel = COMMON ? 2 : (automask ? (avg ? 1 : S) : 0);   // identity candidates of the selection
+    const int n_sel = COMMON ? (MODE == 0 ? 2 : S) : (automask ? (avg ? 1 : S) : 0);   // identity candidates of the selection
     const int n_id = (mode == 0) ? n_sel : 0;             // ... evaluated by this launch
-    const int fa = COMMON ? 0 : p.f_base;                 // frames in the two halves of every pair
+    const int fa = (COMMON && MODE == 0) ? 0 : p.f_base;  // frames in the two halves of every pair
     const bool two = COMMON ? true : p.pair_n > 1;
     const int fb = two ? fa + 1 : fa;                     // one frame: it is aliased into the second half
 
@@ -226,6 +227,8 @@ sweep_kernel(const PhotoParams p) {
     const float* __restrict__ disp_g = ps.disp;
     const float* __restrict__ id_g = p.identity;
     const float* __restrict__ nz_g = COMMON ? nullptr : ps.noise;
+    const float* __restrict__ fw_g = COMMON ? nullptr : ps.fw;      // predictive mask and its gradient
+    float* __restrict__ gfw_g = COMMON ? nullptr : ps.gfw;
     const int b3p = b * 3 * plane;          // image offset in a [B,3,H,W] tensor
     const int bdp = b * hd * wd;            // ... in disp_s / grad_disp_s
     const int bip = b * n_id * plane;       // ... in the identity-loss / noise tensors
@@ -559,8 +562,8 @@ sweep_kernel(const PhotoParams p) {
                 const int idx = ps.argmin[bp + py * W + cx];
                 if (avg) wgt = (idx == n_sel) ? f2(1.0f / (float)S, two ? 1.0f / (float)S : 0.f) : splat(0.f);
                 else wgt = f2(idx == n_sel + fa ? 1.f : 0.f, (two && idx == n_sel + fb) ? 1.f : 0.f);
-                if (ps.fw != nullptr) {   // predictive mask (trainer.py:579): d (rp * m) / d rp = m
-                    const float* mq = at(ps.fw, (b * S + fa) * plane + py * W + cx);
+                if (fw_g != nullptr) {   // predictive mask (trainer.py:579): d (rp * m) / d rp = m
+                    const float* mq = at(fw_g, (b * S + fa) * plane + py * W + cx);
                     wgt = mul2(wgt, f2(__ldg(mq), two ? __ldg(at(mq, plane)) : 0.f));
                 }
             }
@@ -573,9 +576,9 @@ sweep_kernel(const PhotoParams p) {
                 for (int i = 0; i < n_sel; i += 2) {
                     float n0 = 0.f, n1 = 0.f;
                     const int o = (b * n_sel + i) * plane + pix;
-                    if (ps.noise != nullptr) {
-                        n0 = __ldg(at(ps.noise, o));
-                        if (i + 1 < n_sel) n1 = __ldg(at(ps.noise, o + plane));
+                    if (nz_g != nullptr) {
+                        n0 = __ldg(at(nz_g, o));
+                        if (i + 1 < n_sel) n1 = __ldg(at(nz_g, o + plane));
                     } else {
                         philox2_normal2((uint32_t)p.seed ^ ((uint32_t)(p.seed >> 32) * 0x9E3779B9u), (uint32_t)(bp + pix),
                                         (uint32_t)pass_i + 0x10000u * (uint32_t)(i >> 1), n0, n1);
@@ -590,7 +593,7 @@ sweep_kernel(const PhotoParams p) {
                 // reprojection losses of the pairs swept before (mode 1), in frame order, then this pair;
                 // the predictive mask weighs every frame (trainer.py:579)
                 const float* rq = p.rp + ((size_t)(pass_i * S) * p.B + b) * plane + pix;   // frame stride: B * plane
-                const float* mq = (ps.fw != nullptr) ? at(ps.fw, b * S * plane + pix) : nullptr;
+                const float* mq = (fw_g != nullptr) ? at(fw_g, b * S * plane + pix) : nullptr;
                 float rsum = 0.f;
                 for (int f = 0; f < fa; ++f) {
                     float r = __ldg(at(rq, f * p.B * plane));
@@ -612,8 +615,8 @@ sweep_kernel(const PhotoParams p) {
                 if (col_owned && py >= y0 && py < y1) {
                     loss_acc += best;
                     if (ps.argmin != nullptr) ps.argmin[bp + pix] = (uint8_t)best_i;
-                    if (ps.gfw != nullptr) {   // d mean(to_optimise) / d mask_f = [f selected] * rp_f / N
-                        float* gq = at(ps.gfw, b * S * plane + pix);
+                    if (gfw_g != nullptr) {   // d mean(to_optimise) / d mask_f = [f selected] * rp_f / N
+                        float* gq = at(gfw_g, b * S * plane + pix);
                         for (int f = 0; f < fa; ++f) {
                             const float sel = avg ? (best_i == n_sel ? 1.0f / (float)S : 0.f) : (best_i == n_sel + f ? 1.f : 0.f);
                             *at(gq, f * plane) = sel * __ldg(at(rq, f * p.B * plane)) * p.inv_n;
