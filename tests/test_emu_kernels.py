@@ -109,3 +109,16 @@ def test_product_refuses_cpu_tensors_without_emulator():
         emulator = False
     with pytest.raises(RuntimeError, match="no CPU path"):
         functional._check(torch.zeros(1), "x", Fake())
+
+
+def test_depth_by_product_without_warped_images(emu_lib):
+    """Default drop-in configuration (no warped images): outputs[("depth", 0, s)] comes from the layer
+    kernels, the sweep runs without by-product stores; same values as the oracle (trainer.py:480)."""
+    variant, opt, inputs, outputs, r32, r64, seed = common.load_golden("trainer_default")
+    got = common.run_product(opt, inputs, outputs, variant, device="cpu", noise_seed=seed,
+                             extra_opt=dict(pml_emit_warped=False, pml_emit_depth="all"))
+    ref = parity.oracle_pair(opt, variant, inputs, outputs, seed)
+    for s in opt.scales:
+        assert common.rel_err(got["depth/%d" % s], ref["depth/%d" % s]) < 1e-5
+        assert "color/-1/%d" % s not in got
+    parity.check(got, opt, variant, inputs, outputs, seed, r32, r64)
