@@ -367,14 +367,19 @@ sweep_kernel(const PhotoParams p) {
 
         // ---- issue the 24 taps of row r; they are consumed after the adjoint below ----
         float2 nw[3], ne[3], sw[3], se[3];
+        {
+            // one address from the (uniform) tensor base per frame, the other five chained from it in
+            // registers: base + index from a uniform base costs two instructions, register + index one
+            const float* a0 = at(src0_g, o0);
+            const float* a1 = at(src1_g, o1);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float* a0 = at(src0_g, o0 + c * plane);
-            const float* a1 = at(src1_g, o1 + c * plane);
-            const float* w0 = at(src0_g, o0 + (c * plane + W));
-            const float* w1 = at(src1_g, o1 + (c * plane + W));
-            nw[c] = f2(__ldg(a0), __ldg(a1)); ne[c] = f2(__ldg(a0 + 1), __ldg(a1 + 1));
-            sw[c] = f2(__ldg(w0), __ldg(w1)); se[c] = f2(__ldg(w0 + 1), __ldg(w1 + 1));
+            for (int c = 0; c < 3; ++c) {
+                const float* w0 = at(a0, W);
+                const float* w1 = at(a1, W);
+                nw[c] = f2(__ldg(a0), __ldg(a1)); ne[c] = f2(__ldg(a0 + 1), __ldg(a1 + 1));
+                sw[c] = f2(__ldg(w0), __ldg(w1)); se[c] = f2(__ldg(w0 + 1), __ldg(w1 + 1));
+                if (c < 2) { a0 = at(a0, plane); a1 = at(a1, plane); }
+            }
         }
 
         // ============ (C) adjoint for the pixels of row r-3, while the taps are in flight ==========
