@@ -118,9 +118,17 @@ __device__ __forceinline__ void philox2_normal2(uint32_t key, uint32_t c0, uint3
         key += 0x9E3779B9u;
     }
     const float k = 2.3283064365386963e-10f;            // 2^-32
-    const float u1 = ((float)c0 + 1.0f) * k;            // (0,1]
+    const float u1 = ((float)c0 + 1.0f) * k;            // (0,1], never subnormal
     const float ang = ((float)c1 * k - 0.5f) * 6.283185307179586f;   // [-pi, pi)
-    const float rad = sqrtf(-2.0f * __logf(u1));
+#ifdef PML_HOST_EMU
+    const float rad = sqrtf(-2.0f * logf(u1));
+#else
+    // MUFU.LG2 / MUFU.SQRT directly: the libm-style wrappers carry subnormal and slow-path handling
+    // (a CALL in the hot loop) that this argument range never needs
+    float lg, rad;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u1));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(lg * -1.3862943611198906f));   // -2 ln 2 * log2(u1)
+#endif
     float sn, cs;
     __sincosf(ang, &sn, &cs);
     n0 = rad * cs;

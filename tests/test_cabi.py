@@ -56,6 +56,26 @@ def test_argument_validation_without_gpu(lib):
     assert lib.dll.pml_ssim_fwd(None, None, None, 1, 8, 8, None) == -1
     assert lib.dll.pml_pose_fwd(None, None, None, 1, 0, None) == -1
     assert lib.dll.pml_smooth_fwd(None, None, None, None, 0, 1, 3, 8, 8, None) == -1
+    # entry points added for the predictive mask and the input pyramid
+    assert lib.dll.pml_upsample_fwd(None, None, 1, 4, 4, 8, 8, None) == -1
+    assert lib.dll.pml_upsample_bwd(None, None, 1, 4, 4, 8, 8, None) == -1
+    assert lib.dll.pml_bce_ones_fwd(None, 16, None, None, 0, None) == -1
+    assert lib.dll.pml_bce_ones_bwd(None, None, None, 16, None) == -1
+    assert lib.dll.pml_bce_workspace_bytes() > 0
+    assert lib.dll.pml_pyramid_u8(None, 1, 32, 64, 4, None, None, 0, None) == -1
+    assert lib.dll.pml_pyramid_workspace_bytes(2, 32, 64, 4) >= 2 * (16 * 32 + 8 * 16) * 3
+    # a frame weight (predictive mask) without PML_FLAG_NO_AUTOMASK is refused (trainer.py:556 / :571)
+    buf = (ctypes.c_float * 4)()
+    q = _cabi.PmlProblem()
+    q.B, q.H, q.W, q.S, q.n_pass = 1, 32, 64, 2, 1
+    addr = ctypes.addressof(buf)
+    q.target = q.K = q.inv_K = q.losses = addr
+    q.sources[0] = q.sources[1] = q.T[0] = q.T[1] = addr
+    q.passes[0].hd, q.passes[0].wd = 32, 64
+    q.passes[0].disp = q.passes[0].smooth_color = q.passes[0].frame_weight = addr
+    assert lib.dll.pml_workspace_bytes(ctypes.byref(q)) == 0
+    q.flags = _cabi.PML_FLAG_NO_AUTOMASK
+    assert lib.dll.pml_workspace_bytes(ctypes.byref(q)) > 0
 
 
 def test_missing_library_fails_loudly(tmp_path):
