@@ -125,6 +125,131 @@ pyramid_level_kernel(const PyramidLevelParams q) {
     }
 }
 
+// -------------------------------------------------------------------------------------------------
+// Packed version of the level kernel (used when the parent width is a multiple of 4, i.e. every
+// level of the reference's sizes): the parent window is de-interleaved into one byte plane per
+// channel while it is staged, so the 12 taps of an output are 12 CONSECUTIVE bytes = 3 words, and a
+// pass is 9 DP4A: the 22-bit coefficients are split into three 8-bit limbs (k = k0 + 2^8 k1 + 2^16 k2,
+// k0, k1 unsigned, k2 signed) -- exact integer arithmetic, same result as the scalar sum.  The cut
+// windows at the image border use the same code with zero-padded 12-tap coefficient vectors (the
+// host shifts each border set to the interior window origin), positions outside the image hold 0.
+// -------------------------------------------------------------------------------------------------
+struct ResampleLimbs { uint32_t w[7][3][3]; };   // [set][limb][word]: 12 taps, 4 per word
+struct PyramidPackedParams {
+    const uint8_t* parent;   // [N, 2h, 2w, 3]
+    uint8_t* child;          // [N, h, w, 3] (nullable for the last level)
+    float* child_f;          // [N, 3, h, w]
+    int N, h, w;
+    ResampleLimbs lx, ly;
+};
+
+constexpr int kPkIW = 80;                    // staged parent columns: 2 * 32 + 16 (origin 2 * ox0 - 8)
+constexpr int kPkIH = 2 * kPyrTOH + 16;      // staged parent rows: origin 2 * oy0 - 8
+constexpr int kPkTmpStride = 52;             // bytes per (channel, column) in the transposed intermediate: 13 words
+
+__device__ __forceinline__ uint32_t pk_dp4a_uu(uint32_t a, uint32_t b, uint32_t c) {
+#ifdef PML_HOST_EMU
+    for (int i = 0; i < 4; ++i) c += ((a >> (8 * i)) & 255u) * ((b >> (8 * i)) & 255u);
+    return c;
+#else
+    return __dp4a(a, b, c);
+#endif
+}
+__device__ __forceinline__ int pk_dp4a_us(uint32_t a, uint32_t b, int c) {   // unsigned bytes of a x signed bytes of b
+#ifdef PML_HOST_EMU
+    for (int i = 0; i < 4; ++i) c += (int)((a >> (8 * i)) & 255u) * (int)(int8_t)((b >> (8 * i)) & 255u);
+    return c;
+#else
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+#endif
+}
+__device__ __forceinline__ uint32_t pk_shift(uint32_t lo, uint32_t hi, int bytes) {   // bytes in 1..3
+#ifdef PML_HOST_EMU
+    return (lo >> (8 * bytes)) | (hi << (32 - 8 * bytes));
+#else
+    return __funnelshift_r(lo, hi, 8 * bytes);
+#endif
+}
+// 12 taps starting at byte `off` (off & 3 in {1, 3}) of a word-aligned byte row
+__device__ __forceinline__ int pk_sample(const uint32_t* row_words, int off, const uint32_t (&k)[3][3]) {
+    const uint32_t* p = row_words + (off >> 2);
+    const int sh = off & 3;
+    const uint32_t a = p[0], b = p[1], c = p[2], d = p[3];
+    const uint32_t t0 = pk_shift(a, b, sh), t1 = pk_shift(b, c, sh), t2 = pk_shift(c, d, sh);
+    uint32_t s0 = pk_dp4a_uu(t0, k[0][0], 0u); s0 = pk_dp4a_uu(t1, k[0][1], s0); s0 = pk_dp4a_uu(t2, k[0][2], s0);
+    uint32_t s1 = pk_dp4a_uu(t0, k[1][0], 0u); s1 = pk_dp4a_uu(t1, k[1][1], s1); s1 = pk_dp4a_uu(t2, k[1][2], s1);
+    int s2 = pk_dp4a_us(t0, k[2][0], 0); s2 = pk_dp4a_us(t1, k[2][1], s2); s2 = pk_dp4a_us(t2, k[2][2], s2);
+    const int acc = (1 << (kResampleBits - 1)) + (int)s0 + (int)(s1 << 8) + (int)((uint32_t)s2 << 16);
+    return clip8(acc);
+}
+
+__global__ void __launch_bounds__(256)
+pyramid_level_packed_kernel(const PyramidPackedParams q) {
+    __shared__ uint32_t s_pl[3][kPkIH][kPkIW / 4];                         // de-interleaved parent window
+    __shared__ uint32_t s_tmp[3][kPyrTOW][kPkTmpStride / 4];                // horizontal pass, transposed: [ch][ox][row]
+    __shared__ float s_div[256];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = blockIdx.z, oy0 = blockIdx.y * kPyrTOH, ox0 = blockIdx.x * kPyrTOW;
+    const int h = q.h, w = q.w, ph = 2 * q.h, pw = 2 * q.w;
+    s_div[tid] = __fdiv_rn((float)tid, 255.0f);
+    const int wy0 = 2 * oy0 - 8, wx0 = 2 * ox0 - 8;                        // window origin (may be negative)
+    const uint8_t* src = q.parent + ((size_t)n * ph * pw) * 3;
+    // ---- stage + de-interleave: one task = 4 pixels = 3 aligned words in, one word per channel out
+    for (int t = tid; t < kPkIH * (kPkIW / 4); t += 256) {
+        const int r = t / (kPkIW / 4), g = t - r * (kPkIW / 4);
+        const int y = wy0 + r, x = wx0 + 4 * g;
+        uint32_t cr = 0u, cg = 0u, cb = 0u;
+        if (y >= 0 && y < ph && x >= 0 && x < pw) {                        // pw % 4 == 0: a group is inside or outside as a whole
+            const uint32_t* pwd = reinterpret_cast<const uint32_t*>(src + ((size_t)y * pw + x) * 3);
+            const uint32_t a = __ldg(pwd), b = __ldg(pwd + 1), c = __ldg(pwd + 2);
+            // bytes: r0 g0 b0 r1 | g1 b1 r2 g2 | b2 r3 g3 b3
+            cr = (a & 255u) | ((a >> 24) << 8) | (((b >> 16) & 255u) << 16) | (((c >> 8) & 255u) << 24);
+            cg = ((a >> 8) & 255u) | ((b & 255u) << 8) | ((b >> 24) << 16) | (((c >> 16) & 255u) << 24);
+            cb = ((a >> 16) & 255u) | (((b >> 8) & 255u) << 8) | ((c & 255u) << 16) | ((c >> 24) << 24);
+        }
+        s_pl[0][r][g] = cr; s_pl[1][r][g] = cg; s_pl[2][r][g] = cb;
+    }
+    __syncthreads();
+    const int xx = ox0 + lane;
+    // ---- horizontal pass: lane = output column, warps stride over (row, channel)
+    {
+        const int setx = resample_set(min(xx, w - 1), w);
+        uint32_t kx[3][3];
+#pragma unroll
+        for (int l = 0; l < 3; ++l)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) kx[l][j] = q.lx.w[setx][l][j];
+        uint8_t* tmp_b = reinterpret_cast<uint8_t*>(&s_tmp[0][0][0]);
+        for (int t = warp; t < kPkIH * 3; t += 8) {
+            const int r = t / 3, ch = t - r * 3;
+            const int y = wy0 + r;
+            int v = 0;
+            if (xx < w && y >= 0 && y < ph) v = pk_sample(&s_pl[ch][r][0], 2 * lane + 3, kx);   // taps 2xx-5.. = window byte 2*lane+3
+            tmp_b[(ch * kPyrTOW + lane) * kPkTmpStride + r] = (uint8_t)v;
+        }
+    }
+    __syncthreads();
+    // ---- vertical pass + ToTensor: lane = output column, warps stride over (output row, channel)
+    if (xx < w) {
+        for (int t = warp; t < kPyrTOH * 3; t += 8) {
+            const int oy = t / 3, ch = t - oy * 3;
+            const int yy = oy0 + oy;
+            if (yy >= h) continue;
+            const int sety = resample_set(yy, h);
+            uint32_t ky[3][3];
+#pragma unroll
+            for (int l = 0; l < 3; ++l)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) ky[l][j] = q.ly.w[sety][l][j];
+            const int v = pk_sample(&s_tmp[ch][lane][0], 2 * oy + 3, ky);
+            if (q.child) q.child[(((size_t)n * h + yy) * w + xx) * 3 + ch] = (uint8_t)v;
+            q.child_f[(((size_t)n * 3 + ch) * h + yy) * w + xx] = s_div[v];
+        }
+    }
+}
+
 // scale 0: ToTensor only.  frames [N,H,W,3] uint8 -> out [N,3,H,W] fp32; one thread per 4 pixels
 // (three aligned words in, three float4 out) when H*W is a multiple of 4, else one per pixel.
 __global__ void __launch_bounds__(256)
