@@ -1,0 +1,31 @@
+"""Memory-safety sweep of the kernel sources: the host-emulator build compiled with AddressSanitizer
+(tests/emu/run_asan.sh) executes the fused paths, the pyramid kernels and the layer kernels on shapes
+that exercise strip / chunk / tile borders.  compute-sanitizer is not available on the GPU pool, so
+this is the out-of-bounds check of the kernel indexing.  TEST INFRASTRUCTURE (optional, a few minutes)."""
+import sys, os
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch, numpy as np
+from ssde_b200 import _cabi, synthetic, functional as Fn
+lib = _cabi.Library(os.environ["PML_EMU_ASAN_LIB"], emulator=True); _cabi.set_library_for_testing(lib)
+import common, parity
+# fused path: golden default, predmask, gru, wide (multi strip / chunk), 5 sources with stereo, S=8, odd sizes
+for name in ("trainer_default", "trainer_predmask", "trainer_wide", "gru_seq3", "trainer_v1multiscale"):
+    variant, opt, inputs, outputs, r32, r64, seed = common.load_golden(name)
+    got = common.run_product(opt, inputs, outputs, variant, device="cpu", noise_seed=seed)
+    print(name, "ok", float(got["loss"]))
+os.environ["PML_KERNEL"] = "sweep"
+for sources, (B, H, W) in (((-1, 1, -2, 2, "s"), (1, 32, 64)), ((-1, 1, -2, 2, -3, 3, -4, 4), (1, 32, 64)), ((-1, 1), (3, 40, 104)), ((1,), (2, 24, 40))):
+    opt = synthetic.make_options(H, W, batch_size=B, scales=[0, 1, 2] if H % 8 else [0, 1, 2, 3])
+    inputs, outputs = synthetic.make_batch(B, H, W, sources=sources, seed=6, scales=opt.scales)
+    got = common.run_product(opt, inputs, outputs, "trainer", device="cpu", noise_seed=None, sources=sources)
+    print(sources, (B, H, W), "ok", float(got["loss"]))
+# pyramid: packed + scalar kernels, border tiles, non-multiple tile sizes
+rng = np.random.default_rng(0)
+for (N, H, W, n) in ((2, 96, 160, 4), (1, 32, 64, 4), (1, 8, 16, 4), (1, 40, 72, 2), (3, 192, 640, 4)):
+    fr = torch.from_numpy(rng.integers(0, 256, (N, H, W, 3), dtype=np.uint8))
+    out = Fn.color_pyramid(fr, n)
+    print("pyramid", (N, H, W, n), "ok", float(out[-1].mean()))
+import layer_checks
+layer_checks.run("cpu"); layer_checks.depth_metrics("cpu")
+print("layers ok")
