@@ -77,7 +77,7 @@ int validate(const pml_problem* p, bool grad) {
 // S=4 at the headline size: 1.4 vs 3.9 ms -- which is kept as an independent implementation for the
 // cross-check test.  PML_KERNEL=cta forces it.
 bool use_sweep(const pml_problem* p) {
-    if (p->pass[0].frame_weight) return true;   // predictive mask: pair sweeps around select_kernel
+    if (p->pass[0].frame_weight) return true;   // predictive mask: handled by the MODE 3 / MODE 2 sweeps
     const char* k = getenv("PML_KERNEL");
     if (p->S > 4) return true;                  // the CTA-strip kernel is instantiated for S <= 4
     if (k && k[0] == 'c') return false;

@@ -49,10 +49,11 @@ struct PhotoParams {
     int n_items;      // total work items (pml_sweep.cuh: one per warp)
     // pml_sweep.cuh with more than two source frames: the frames are swept pair by pair
     int mode;         // 0: selection in the sweep (S <= 2); 1: reprojection losses only -> rp;
-                      // 2: selection given by pass.argmin (written by select_kernel)
+                      // 2: selection given by pass.argmin (written by the mode-3 sweep);
+                      // 3: last pair: selection over identity + rp of earlier pairs + own pair
     int f_base;       // first frame of the pair handled by this launch
     int pair_n;       // frames in the pair: 1 or 2
-    float* rp;        // [n_pass][S][B][H][W] reprojection losses (modes 1 / select_kernel)
+    float* rp;        // [n_pass][S][B][H][W] reprojection losses (written in mode 1, read in mode 3)
     float* part;      // [n_cta][part_stride]: loss partial, then S x 12 dL/dP partials
     int part_stride;
     float inv_n;      // 1 / (B*H*W)

@@ -566,7 +566,7 @@ sweep_kernel(const PhotoParams p) {
                 if (two) rq[(size_t)p.B * plane] = rp.y;
             }
         } else if (mode == 2) {
-            // ... second sweep: the selection was made by select_kernel over all frames
+            // ... adjoint sweep of an earlier pair: the selection was made by the last pair's sweep (mode 3)
             if (p_valid) {
                 const int idx = ps.argmin[bp + py * W + cx];
                 if (avg) wgt = (idx == n_sel) ? f2(1.0f / (float)S, two ? 1.0f / (float)S : 0.f) : splat(0.f);

@@ -48,7 +48,7 @@ def test_three_sources_with_stereo(emu_lib):
                                           ((-1, 1, -2, 2, -3, 3, -4, 4), {}), ((-1, 1, -2, 2, "s"), {}),
                                           ((-1, 1, -2), dict(disable_automasking=True)), ((-1, 1, -2, 2), dict(no_ssim=True))])
 def test_more_than_two_sources_pair_sweeps(emu_lib, sources, over, monkeypatch):
-    # S > 2: forward sweep per frame pair -> select_kernel -> forward+adjoint sweep per pair
+    # S > 2: forward sweeps of all pairs but the last -> last pair's sweep selects -> adjoint sweeps of the others
     # (three frames default to the CTA-strip kernel; force the pair sweeps here)
     monkeypatch.setenv("PML_KERNEL", "sweep")
     B, H, W = 1, 32, 64
