@@ -13,6 +13,9 @@ ours:       value    = CUDA-graph replay of the step with inputs resident in HBM
             e2e      = the reference-facing drop-in call (Trainer.generate_images_pred +
                        compute_losses + backward), inputs in pinned HOST memory, H2D copies and the
                        D2H read of the loss inside the timed region.
+            e2e_u8_ingest = the same loop fed with the uint8 scale-0 frames the image decoder delivers;
+                       trainer_hooks.ingest_colors builds the fp32 colour pyramid on the device (bit-exact
+                       with the reference's PIL + ToTensor preprocessing), 3.2x fewer bytes on the link.
             roofline = algorithmic bytes of the fused sweep kernel / its CUDA-event duration.
             cpu_baseline = the CPU oracle (port of the reference's ATen recipe) on the host cores.
 reference:  the reference's own CPU implementation of the path.  /root/reference is pure Python
