@@ -548,11 +548,7 @@ sweep_kernel(const PhotoParams p) {
         if (mode == 0 && n_id > 0 && nz_g == nullptr) {
             const float m_id = (n_id > 1) ? fminf(idv0, idv1) : idv0;
             const float m_rp = avg ? (two ? (rp.x + rp.y) * 0.5f : rp.x) : (two ? fminf(rp.x, rp.y) : rp.x);
-            // noise can only matter if an identity candidate can come out on top (best identity within the
-            // bound of the best reprojection loss, or below it), and then only if that contest is close
-            // or the two identity candidates are close to each other (their order decides the index)
-            const bool close = (m_id - m_rp < 1.4e-4f) &&
-                               ((m_rp - m_id < 1.4e-4f) || (n_id > 1 && fabsf(idv0 - idv1) < 1.4e-4f));
+            const bool close = (n_id > 1 && fabsf(idv0 - idv1) < 1.4e-4f) || (fabsf(m_id - m_rp) < 1.4e-4f);
             if (__any_sync(0xffffffffu, close && p_valid))
                 philox2_normal2((uint32_t)p.seed ^ ((uint32_t)(p.seed >> 32) * 0x9E3779B9u),
                                 (uint32_t)(bp + py * W + cx), (uint32_t)pass_i, nzv0, nzv1);
