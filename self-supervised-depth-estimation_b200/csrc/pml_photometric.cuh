@@ -626,17 +626,25 @@ finalize_image_kernel(const FinalizeParams q) {
     const int ncol = q.with_grad ? 1 + 12 * q.S : 1;
     // photometric partial columns of this image's work items (up to 1 + 12 * 8 = 97): two interleaved
     // segments per column, each summed in item order, then combined (fixed order => deterministic)
+    // (up to 32 columns, i.e. S <= 2: eight segments of 32 columns -- four times shorter dependent chains)
+    const bool narrow = ncol <= 32;
     {
-        const int col = tid & 127, seg = tid >> 7;
+        const int col = narrow ? (tid & 31) : (tid & 127), seg = narrow ? (tid >> 5) : (tid >> 7);
+        const int nseg = narrow ? 8 : 2;
         float v = 0.f;
         if (col < ncol) {
             const float* base = q.part + (size_t)(pi * q.cta_per_pass + b * q.cta_per_image) * q.part_stride + col;
-            for (int c = seg; c < q.cta_per_image; c += 2) v += base[(size_t)c * q.part_stride];
+            for (int c = seg; c < q.cta_per_image; c += nseg) v += base[(size_t)c * q.part_stride];
         }
-        s_seg[seg][col] = v;
+        s_seg[0][tid] = v;     // flat [segment][column]: 8 x 32 or 2 x 128
     }
     __syncthreads();
-    if (tid < ncol) s_col[tid] = s_seg[0][tid] + s_seg[1][tid];
+    if (tid < ncol) {
+        float t = 0.f;
+        if (narrow) { for (int g = 0; g < 8; ++g) t += s_seg[0][g * 32 + tid]; }
+        else t = s_seg[0][tid] + s_seg[0][128 + tid];
+        s_col[tid] = t;
+    }
     // smoothness partials of this image
     const int nb = q.smooth_blocks[pi];
     const float* sp = q.smooth_part + ((size_t)q.smooth_off[pi] + (size_t)b * nb) * 3;
