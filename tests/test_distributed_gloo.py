@@ -47,10 +47,16 @@ def _worker(rank, world, port, emu_path, ret):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     gathered = [torch.zeros_like(disps[0].grad) for _ in range(world)]
     dist.all_gather(gathered, disps[0].grad)
+    # input pyramid: every rank ingests the uint8 frames of its own images
+    frames = torch.randint(0, 256, (B, H, W, 3), generator=torch.Generator().manual_seed(3), dtype=torch.uint8)
+    lvl = Fn.color_pyramid(frames[sl], 3)[2]
+    pyr = [torch.zeros_like(lvl) for _ in range(world)]
+    dist.all_gather(pyr, lvl)
     if rank == 0:
         ret["loss"] = l.item()
         ret["tmax"] = t.item()
         ret["grad0"] = torch.cat(gathered, 0) / world
+        ret["pyr2"] = torch.cat(pyr, 0)
     dist.destroy_process_group()
 
 
@@ -69,3 +75,9 @@ def test_two_rank_sharding_matches_single_process(emu_lib):
     assert abs(ret["loss"] - full["loss"].item()) / abs(full["loss"].item()) < 1e-6
     assert ret["tmax"] == 2.0
     assert common.rel_err(ret["grad0"], full["grad_disp/0"]) < 1e-5
+    # the sharded pyramid equals the single-process one bit for bit (and the numpy oracle)
+    from ssde_b200 import functional as Fn
+    from oracle import pyramid_oracle as pyo
+    frames = torch.randint(0, 256, (B, H, W, 3), generator=torch.Generator().manual_seed(3), dtype=torch.uint8)
+    assert torch.equal(ret["pyr2"], Fn.color_pyramid(frames, 3)[2])
+    assert (ret["pyr2"].numpy() == pyo.pyramid(frames.numpy(), 3)[0][2]).all()
