@@ -303,6 +303,10 @@ def run(opt, inputs, outputs, sources=(-1, 1), variant="trainer", noise=None, dt
             if f != "s":
                 out[("cam_T_cam", 0, f)].requires_grad_(True)
                 leaves["grad_T/{}".format(f)] = out[("cam_T_cam", 0, f)]
+                if variant == "trainer" and opt.pose_model_type == "posecnn":   # trainer.py:490-499
+                    for k in ("axisangle", "translation"):
+                        out[(k, 0, f)].requires_grad_(True)
+                        leaves["grad_{}/{}".format(k, f)] = out[(k, 0, f)]
     nz = None if noise is None else [conv(n) for n in noise]
     generate_images_pred(opt, inp, out, sources, variant)
     losses = compute_losses(opt, inp, out, sources, variant, nz, keep_maps=keep_maps,

@@ -125,14 +125,18 @@ def run(opt, inputs, outputs, variant="trainer", noise_seed=0, dtype=torch.float
         for f in (-1, 1):
             out[("cam_T_cam", 0, f)].requires_grad_(True)
             leaves["grad_T/{}".format(f)] = out[("cam_T_cam", 0, f)]
+            if variant == "trainer" and getattr(opt, "pose_model_type", "") == "posecnn":   # trainer.py:490-499
+                for k in ("axisangle", "translation"):
+                    out[(k, 0, f)].requires_grad_(True)
+                    leaves["grad_{}/{}".format(k, f)] = out[(k, 0, f)]
 
     torch.manual_seed(noise_seed)
     # trainer.py:582 builds its BCE target with torch.ones(...) in the DEFAULT dtype, so the float64
     # run of the predictive-mask branch needs the default switched (that branch draws no noise, so
     # the generator stream of the other cases is not affected)
     old_default = torch.get_default_dtype()
-    if "predictive_mask" in out:
-        torch.set_default_dtype(dtype)
+    if "predictive_mask" in out or (getattr(opt, "pose_model_type", "") == "posecnn" and opt.disable_automasking):
+        torch.set_default_dtype(dtype)     # posecnn: layers.get_translation_matrix uses torch.zeros (layers.py:51)
     try:
         with _RecordMin() as rec:
             Trainer.generate_images_pred(ns, inp, out)

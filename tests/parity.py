@@ -137,7 +137,7 @@ def check(got, opt, variant, inputs, outputs, seed, ref32=None, ref64=None, sour
                 a, b = a * keep, b * keep
             e, e2 = common.rel_err(a, b), l2_err(a, b)
             f, f2 = fam[k.split("/")[0]]
-            if k.startswith("grad_T"):
+            if k.startswith(("grad_T", "grad_axisangle", "grad_translation")):   # sums over all pixels (posecnn: through T)
                 f, f2 = f + amb_share, f2 + amb_share
             rep[k] = (e, e2)
             assert e <= GRAD_TOL + 2 * f, "%s: max-norm rel err %.3e (fp32 reference itself %.3e)" % (k, e, f)

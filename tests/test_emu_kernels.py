@@ -10,7 +10,7 @@ import parity
 from ssde_b200 import synthetic, functional, layers as L, _cabi
 
 CASES = ["trainer_default", "trainer_avg", "trainer_nossim", "trainer_v1multiscale", "gru_seq3",
-         "fusion_default", "trainer_static", "trainer_predmask", "trainer_predmask_avg"]
+         "fusion_default", "trainer_static", "trainer_predmask", "trainer_predmask_avg", "trainer_posecnn"]
 
 
 @pytest.mark.parametrize("name", CASES)

@@ -47,7 +47,7 @@ def test_golden_covers_every_variant_and_flag():
     names = set(common.golden_names())
     for need in ("trainer_default", "trainer_avg", "trainer_noautomask", "trainer_nossim", "trainer_v1multiscale",
                  "fusion_default", "fusion_v3_default", "gru_seq3", "trainer_static", "trainer_constant", "trainer_oof",
-                 "trainer_predmask", "trainer_predmask_avg"):
+                 "trainer_predmask", "trainer_predmask_avg", "trainer_posecnn"):
         assert need in names
 
 
