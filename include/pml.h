@@ -30,6 +30,9 @@
 extern "C" {
 #endif
 
+/* ABI history: 1 = fused loss + layer kernels + depth metrics; 2 = pml_pass.frame_weight / grad_frame_weight
+ * (predictive mask), pml_upsample_*, pml_bce_ones_*, pml_pyramid_u8; 3 = PML_MAX_SOURCES 4 -> 8 (array sizes in
+ * pml_problem) and pml_problem.loss_vector.  The Python binding refuses a library of another version. */
 #define PML_ABI_VERSION 3
 #define PML_MAX_SOURCES 8 /* source frames per target, e.g. (-1, 1, "s") = 3; BASELINE config 5 sweeps 2/4/8 */
 #define PML_MAX_PASSES 8  /* scales handled by one call */
