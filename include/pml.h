@@ -32,10 +32,14 @@ extern "C" {
 
 /* ABI history: 1 = fused loss + layer kernels + depth metrics; 2 = pml_pass.frame_weight / grad_frame_weight
  * (predictive mask), pml_upsample_*, pml_bce_ones_*, pml_pyramid_u8; 3 = PML_MAX_SOURCES 4 -> 8 (array sizes in
- * pml_problem) and pml_problem.loss_vector.  The Python binding refuses a library of another version. */
-#define PML_ABI_VERSION 3
+ * pml_problem) and pml_problem.loss_vector; 4 = pml_problem.loss_total / loss_total_div (the mean over scales,
+ * trainer.py:621, written by the library), pml_problem.segments (per-timestep tensors of the sequence trainer consumed
+ * in place), pml_scale_grads takes the upstream of the total, pml_selection_masks, PML_FLAG_KERNEL_CTA.
+ * The Python binding refuses a library of another version. */
+#define PML_ABI_VERSION 4
 #define PML_MAX_SOURCES 8 /* source frames per target, e.g. (-1, 1, "s") = 3; BASELINE config 5 sweeps 2/4/8 */
 #define PML_MAX_PASSES 8  /* scales handled by one call */
+#define PML_MAX_SEGMENTS 16 /* separately allocated chunks of the batch (len_sequence of trainer_gru.py, default 10) */
 
 typedef struct CUstream_st* pml_stream_t; /* == cudaStream_t */
 
@@ -51,6 +55,8 @@ typedef enum pml_status {
 #define PML_FLAG_NO_SSIM 1u      /* --no_ssim             trainer.py:523 */
 #define PML_FLAG_NO_AUTOMASK 2u  /* --disable_automasking trainer.py:556 */
 #define PML_FLAG_AVG_REPROJ 4u   /* --avg_reprojection    trainer.py:565,585 */
+#define PML_FLAG_KERNEL_CTA 256u /* testing: run the first-generation CTA-strip kernel (S <= 4, no frame weights)
+                                    instead of the warp-strip sweep; same results, kept as an independent cross-check */
 
 /* One scale ("pass") of the loss: trainer.py:469 / :538 loop body. */
 typedef struct pml_pass {
@@ -72,6 +78,21 @@ typedef struct pml_pass {
                                   (the reference's `elif`), set on every pass or on none */
     float* grad_frame_weight;  /* [B,S,H,W] out: d loss_s / d frame_weight (forward_backward only) */
 } pml_pass;
+
+/* Optional: the image batch arrives as n_seg separately allocated chunks of seg_size images each
+ * (B == n_seg * seg_size).  trainer_gru.py keeps one tensor per time step, inputs[("color", f, s, i)],
+ * inputs[("K", s, i)], and concatenates them on the fly for every scale and frame (trainer_gru.py:890-899,
+ * 943-957); with this table the kernels read the per-timestep tensors in place: image b lives in chunk
+ * b / seg_size at index b % seg_size.  Pointers a problem does not use may be NULL.  When `segments` is set,
+ * pml_problem.target / sources / K / inv_K and pml_pass.smooth_color are ignored.  HOST struct of DEVICE pointers. */
+typedef struct pml_segments {
+    int32_t n_seg, seg_size;
+    const float* target[PML_MAX_SEGMENTS];                        /* [seg_size,3,H,W] each */
+    const float* sources[PML_MAX_SOURCES][PML_MAX_SEGMENTS];      /* [seg_size,3,H,W] */
+    const float* K[PML_MAX_SEGMENTS];                             /* [seg_size,4,4] */
+    const float* inv_K[PML_MAX_SEGMENTS];                         /* [seg_size,4,4] */
+    const float* smooth_color[PML_MAX_PASSES][PML_MAX_SEGMENTS];  /* [seg_size,3,hd,wd] */
+} pml_segments;
 
 /* A group of passes that share images, intrinsics and poses (all scales when
  * v1_multiscale is off; one scale per group when it is on). */
@@ -97,6 +118,11 @@ typedef struct pml_problem {
     void* prof_start;       /* optional cudaEvent_t recorded right before the fused sweep kernel */
     void* prof_stop;        /* optional cudaEvent_t recorded right after it (bench.py roofline) */
     float* loss_vector;     /* [n_pass] out, nullable: loss_s again as a contiguous vector (what autograd returns) */
+    float* loss_total;      /* [1] out, nullable: (loss_0 + loss_1 + ...) / loss_total_div in scale order =
+                               losses["loss"] (trainer.py:618-621) when loss_total_div == num_scales */
+    float loss_total_div;   /* divisor of loss_total; 0 is read as n_pass */
+    int32_t reserved2;
+    const pml_segments* segments; /* nullable, see pml_segments */
 } pml_problem;
 
 int pml_abi_version(void);
@@ -114,10 +140,18 @@ int pml_loss_forward(const pml_problem* p, void* workspace, size_t workspace_byt
 int pml_loss_forward_backward(const pml_problem* p, void* workspace, size_t workspace_bytes, pml_stream_t stream);
 
 /* Backward of the autograd node: grad_disp_s <- up[s] * (grad_disp_s + const[s,b]) in place and
- * grad_T_out[f,b] = sum_s up[s] * grad_T[s,f,b].  `upstream` is a device array [n_pass]. */
+ * grad_T_out[f,b] = sum_s up[s] * grad_T[s,f,b], with up[s] = upstream[s] + upstream_total[0] / total_div.
+ * `upstream` (device [n_pass]) is the gradient arriving at loss_vector, `upstream_total` (device [1]) the one
+ * arriving at loss_total; either may be NULL (read as zero), not both. */
 int pml_scale_grads(int32_t n_pass, int32_t B, int32_t S, const int32_t* hd, const int32_t* wd,
                     float* const* grad_disp, const float* grad_disp_const, const float* grad_T,
-                    const float* upstream, float* grad_T_out, pml_stream_t stream);
+                    const float* upstream, const float* upstream_total, float total_div,
+                    float* grad_T_out, pml_stream_t stream);
+
+/* outputs["identity_selection/{s}"] (trainer.py:606-608) for every scale in one launch:
+ * out[s][i] = argmin[s][i] > n_id - 1 ? 1.f : 0.f over n_pix = B*H*W pixels per scale. */
+int pml_selection_masks(int32_t n_pass, int64_t n_pix, const uint8_t* const* argmin, int32_t n_id,
+                        float* const* out, pml_stream_t stream);
 
 /* ---- layer-level drop-ins (layers.py signatures), each one kernel forward + one backward ---- */
 /* disp_to_depth, layers.py:16-25 */

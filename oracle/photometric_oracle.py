@@ -178,8 +178,8 @@ def generate_images_pred(opt, inputs, outputs, sources=(-1, 1), variant="trainer
                 T = inputs["stereo_T"]
             else:
                 T = outputs[("cam_T_cam", 0, frame_id)]
-            if variant == "trainer" and opt.pose_model_type == "posecnn" and frame_id != "s":
-                # trainer.py:490-499
+            if variant in ("trainer", "fusion") and opt.pose_model_type == "posecnn" and frame_id != "s":
+                # trainer.py:490-499, trainer_fusion.py:446-456 (absent from trainer_fusion_v3 / trainer_gru)
                 axisangle = outputs[("axisangle", 0, frame_id)]
                 translation = outputs[("translation", 0, frame_id)]
                 mean_inv_depth = (1 / depth).mean(3, True).mean(2, True)
@@ -194,13 +194,16 @@ def generate_images_pred(opt, inputs, outputs, sources=(-1, 1), variant="trainer
 
 
 def compute_losses(opt, inputs, outputs, sources=(-1, 1), variant="trainer",
-                   noise: Optional[Sequence[torch.Tensor]] = None, keep_maps=False, forced_argmin=None):
+                   noise: Optional[Sequence[torch.Tensor]] = None, keep_maps=False, forced_argmin=None,
+                   pixel_weight=None):
     """trainer.py:531-622 (trainer_fusion.py:488-579; trainer_fusion_v3.py:498-590;
     trainer_gru.py:926-1023).  ``noise`` = pre-drawn tie-break tensors, one per scale, in the
     order the reference draws them (trainer.py:592-595); None draws from the global generator.
     ``forced_argmin`` ({scale: int64 [B,H,W]}) replaces the min by a gather with the given
     selection: gradients of a candidate path are then comparable even where fp32 rounding of a
     near-tie made the device pick the other candidate (test use only).
+    ``pixel_weight`` ({scale: [B,H,W]}) multiplies the per-pixel photometric term before the mean
+    (test use only: measures how much of a pose gradient a set of pixels carries).
 
     Returns ``losses`` like the reference plus, under ``outputs``: ``identity_selection/{s}``,
     ``("argmin", s)`` (int64 [B,H,W], what the reference's ``torch.min`` returns) and, with
@@ -259,6 +262,8 @@ def compute_losses(opt, inputs, outputs, sources=(-1, 1), variant="trainer",
             else:
                 outputs[("margin", scale)] = torch.full_like(to_opt.detach().reshape(idxs.shape), float("inf"))
 
+        if pixel_weight is not None:
+            to_opt = to_opt.reshape(idxs.shape) * pixel_weight[scale].to(to_opt.dtype)
         loss = extra + to_opt.mean()
         loss = loss + opt.disparity_smoothness * normalised_smooth_loss(disp, color) / (2 ** scale)
         total = total + loss
@@ -278,7 +283,7 @@ def nest_predictive_mask(outputs):
 
 
 def run(opt, inputs, outputs, sources=(-1, 1), variant="trainer", noise=None, dtype=None,
-        want_grad=True, keep_maps=True, forced_argmin=None):
+        want_grad=True, keep_maps=True, forced_argmin=None, pixel_weight=None):
     """Whole path on copies of the dictionaries: fwd (+ bwd of losses["loss"]).
 
     Returns a dict: loss (float), loss/{s}, argmin/{s}, identity_selection/{s}, margin/{s},
@@ -303,14 +308,14 @@ def run(opt, inputs, outputs, sources=(-1, 1), variant="trainer", noise=None, dt
             if f != "s":
                 out[("cam_T_cam", 0, f)].requires_grad_(True)
                 leaves["grad_T/{}".format(f)] = out[("cam_T_cam", 0, f)]
-                if variant == "trainer" and opt.pose_model_type == "posecnn":   # trainer.py:490-499
+                if variant in ("trainer", "fusion") and opt.pose_model_type == "posecnn":   # trainer.py:490-499
                     for k in ("axisangle", "translation"):
                         out[(k, 0, f)].requires_grad_(True)
                         leaves["grad_{}/{}".format(k, f)] = out[(k, 0, f)]
     nz = None if noise is None else [conv(n) for n in noise]
     generate_images_pred(opt, inp, out, sources, variant)
     losses = compute_losses(opt, inp, out, sources, variant, nz, keep_maps=keep_maps,
-                            forced_argmin=forced_argmin)
+                            forced_argmin=forced_argmin, pixel_weight=pixel_weight)
     res = {"loss": losses["loss"].detach()}
     for s in opt.scales:
         res["loss/{}".format(s)] = losses["loss/{}".format(s)].detach()

@@ -8,12 +8,14 @@ import os
 from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t,
                     c_uint32, c_uint64, c_void_p)
 
-PML_ABI_VERSION = 3
+PML_ABI_VERSION = 4
 PML_MAX_SOURCES = 8
 PML_MAX_PASSES = 8
+PML_MAX_SEGMENTS = 16
 PML_FLAG_NO_SSIM = 1
 PML_FLAG_NO_AUTOMASK = 2
 PML_FLAG_AVG_REPROJ = 4
+PML_FLAG_KERNEL_CTA = 256
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_LIB = os.path.join(_HERE, "libpml.so")
@@ -26,6 +28,14 @@ class PmlPass(Structure):
                 ("frame_weight", c_void_p), ("grad_frame_weight", c_void_p)]
 
 
+class PmlSegments(Structure):
+    _fields_ = [("n_seg", c_int32), ("seg_size", c_int32),
+                ("target", c_void_p * PML_MAX_SEGMENTS),
+                ("sources", (c_void_p * PML_MAX_SEGMENTS) * PML_MAX_SOURCES),
+                ("K", c_void_p * PML_MAX_SEGMENTS), ("inv_K", c_void_p * PML_MAX_SEGMENTS),
+                ("smooth_color", (c_void_p * PML_MAX_SEGMENTS) * PML_MAX_PASSES)]
+
+
 class PmlProblem(Structure):
     _fields_ = [("B", c_int32), ("H", c_int32), ("W", c_int32), ("S", c_int32), ("n_pass", c_int32),
                 ("flags", c_uint32), ("min_depth", c_float), ("max_depth", c_float), ("eps", c_float),
@@ -34,7 +44,9 @@ class PmlProblem(Structure):
                 ("K", c_void_p), ("inv_K", c_void_p), ("T", c_void_p * PML_MAX_SOURCES),
                 ("passes", PmlPass * PML_MAX_PASSES),
                 ("losses", c_void_p), ("grad_T", c_void_p), ("grad_disp_const", c_void_p),
-                ("prof_start", c_void_p), ("prof_stop", c_void_p), ("loss_vector", c_void_p)]
+                ("prof_start", c_void_p), ("prof_stop", c_void_p), ("loss_vector", c_void_p),
+                ("loss_total", c_void_p), ("loss_total_div", c_float), ("reserved2", c_int32),
+                ("segments", POINTER(PmlSegments))]
 
 
 class PmlError(RuntimeError):
@@ -48,7 +60,8 @@ _SIGNATURES = {
     "pml_loss_forward": (c_int, [POINTER(PmlProblem), c_void_p, c_size_t, c_void_p]),
     "pml_loss_forward_backward": (c_int, [POINTER(PmlProblem), c_void_p, c_size_t, c_void_p]),
     "pml_scale_grads": (c_int, [c_int32, c_int32, c_int32, POINTER(c_int32), POINTER(c_int32),
-                                POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
+    "pml_selection_masks": (c_int, [c_int32, c_int64, POINTER(c_void_p), c_int32, POINTER(c_void_p), c_void_p]),
     "pml_disp_to_depth_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_void_p]),
     "pml_disp_to_depth_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_void_p]),
     "pml_backproject_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),

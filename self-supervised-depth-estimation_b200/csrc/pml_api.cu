@@ -41,10 +41,50 @@ inline void pml_event_record(void* ev, cudaStream_t st) {
 #endif
 }
 
-int env_int(const char* name, int dflt) {
-    const char* s = getenv(name);
-    return (s && *s) ? atoi(s) : dflt;
-}
+// Developer knobs (A/B experiments on the GPU box).  Read ONCE per process, never on the per-call path.
+struct Knobs {
+    int th, id_th, smem_pad, pyramid_scalar;
+    Knobs() {
+        auto geti = [](const char* name, int dflt) { const char* s = getenv(name); return (s && *s) ? atoi(s) : dflt; };
+        th = geti("PML_TH", 0); id_th = geti("PML_ID_TH", 16); smem_pad = geti("PML_SMEM_PAD", 0);
+        pyramid_scalar = geti("PML_PYRAMID_SCALAR", 0);
+    }
+};
+const Knobs& knobs() { static const Knobs k; return k; }
+
+// RAII: make the device that owns `ptr` current for the duration of an entry point.  The reference trainers keep
+// their tensors on cuda:1 / cuda:3 and never call set_device (trainer.py:44,67); the legacy default stream handle
+// is the same for every device, so without this the kernels would be enqueued on the wrong GPU.
+struct DeviceGuard {
+    int prev = -1, dev = -1;
+    bool switched = false;
+    explicit DeviceGuard(const void* ptr) {
+#ifndef PML_HOST_EMU
+        cudaPointerAttributes a;
+        if (!ptr || cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return; }
+        if (a.type != cudaMemoryTypeDevice && a.type != cudaMemoryTypeManaged) return;   // host pointer: the launch will fault loudly
+        dev = a.device;
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = (cudaSetDevice(dev) == cudaSuccess);
+#else
+        (void)ptr;
+#endif
+    }
+    ~DeviceGuard() {
+#ifndef PML_HOST_EMU
+        if (switched) cudaSetDevice(prev);
+#endif
+    }
+    // true if `other` lives on another device than the guarded pointer (unknown pointers pass)
+    bool foreign(const void* other) const {
+#ifndef PML_HOST_EMU
+        cudaPointerAttributes a;
+        if (dev < 0 || !other || cudaPointerGetAttributes(&a, other) != cudaSuccess) { cudaGetLastError(); return false; }
+        return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) && a.device != dev;
+#else
+        (void)other; return false;
+#endif
+    }
+};
 
 int validate(const pml_problem* p, bool grad) {
     if (!p) return PML_ERR_INVALID;
@@ -56,6 +96,15 @@ int validate(const pml_problem* p, bool grad) {
     if (grad && (!p->grad_T || !p->grad_disp_const)) return PML_ERR_INVALID;
     for (int f = 0; f < p->S; ++f)
         if (!p->sources[f] || !p->T[f]) return PML_ERR_INVALID;
+    if (const pml_segments* sg = p->segments) {   // chunked batch: every chunk of every tensor in use must be there
+        if (sg->n_seg < 1 || sg->n_seg > PML_MAX_SEGMENTS || sg->seg_size < 1 || sg->n_seg * sg->seg_size != p->B) return PML_ERR_INVALID;
+        if (p->flags & PML_FLAG_KERNEL_CTA) return PML_ERR_UNSUPPORTED;
+        for (int j = 0; j < sg->n_seg; ++j) {
+            if (!sg->target[j] || !sg->K[j] || !sg->inv_K[j]) return PML_ERR_INVALID;
+            for (int f = 0; f < p->S; ++f) if (!sg->sources[f][j]) return PML_ERR_INVALID;
+            for (int i = 0; i < p->n_pass; ++i) if (!sg->smooth_color[i][j]) return PML_ERR_INVALID;
+        }
+    }
     for (int i = 0; i < p->n_pass; ++i) {
         const pml_pass& ps = p->pass[i];
         if (!ps.disp || !ps.smooth_color || ps.hd < 2 || ps.wd < 2) return PML_ERR_INVALID;
@@ -75,13 +124,11 @@ int validate(const pml_problem* p, bool grad) {
 // the adjoint sweeps of the others).  It is ahead of the first-generation CTA-strip kernel
 // (pml_photometric.cuh, templated on S <= 4) everywhere -- S=3 at B=8, 320x1024: 2.5 vs 2.8 ms;
 // S=4 at the headline size: 1.4 vs 3.9 ms -- which is kept as an independent implementation for the
-// cross-check test.  PML_KERNEL=cta forces it.
+// cross-check test.  PML_FLAG_KERNEL_CTA selects it.
 bool use_sweep(const pml_problem* p) {
     if (p->pass[0].frame_weight) return true;   // predictive mask: handled by the MODE 3 / MODE 2 sweeps
-    const char* k = getenv("PML_KERNEL");
     if (p->S > 4) return true;                  // the CTA-strip kernel is instantiated for S <= 4
-    if (k && k[0] == 'c') return false;
-    return true;
+    return !(p->flags & PML_FLAG_KERNEL_CTA);
 }
 
 Plan make_plan(const pml_problem* p, bool grad) {
@@ -97,7 +144,7 @@ Plan make_plan(const pml_problem* p, bool grad) {
         double cost = (double)ns * nt / p->W;
         if (cost < best_cost - 1e-9) { best_cost = cost; best_nt = nt; }
     }
-    pl.NT = env_int("PML_NT", best_nt);
+    pl.NT = best_nt;
     if (pl.NT < 64) pl.NT = 64;
     if (pl.NT > 128) pl.NT = 128;
     pl.NT = (pl.NT / 32) * 32;
@@ -117,7 +164,7 @@ Plan make_plan(const pml_problem* p, bool grad) {
         int th = (p->H + want - 1) / want;
         if (th < 16) th = 16;
         th = ((th + 7) / 8) * 8;
-        th = env_int("PML_TH", th);
+        if (knobs().th > 0) th = knobs().th;
         if (th > p->H) th = p->H;
         if (th < 4) th = 4;
         return th;
@@ -188,7 +235,7 @@ int launch_photo(const PhotoParams& pp, int n_cta, int NT, int low_cells, cudaSt
 
 template <bool GRAD, bool SSIM>
 int launch_sweep(const PhotoParams& pp, cudaStream_t st) {
-    const size_t smem = sweep_smem_bytes() + (size_t)env_int("PML_SMEM_PAD", 0);   // < 48 KB: no opt-in needed
+    const size_t smem = sweep_smem_bytes() + (size_t)knobs().smem_pad;   // < 48 KB: no opt-in needed
     if (pp.B > 65535) return PML_ERR_UNSUPPORTED;
     const dim3 grid(pp.n_chunks * pp.n_strips, pp.B, pp.n_pass);
     bool emit = false;   // by-products requested by any pass (never in sweep mode 2)
@@ -231,6 +278,9 @@ int dispatch_S(int S, const PhotoParams& pp, int n_cta, int NT, int low_cells, c
 int run_loss(const pml_problem* p, void* ws, size_t ws_bytes, cudaStream_t st, bool grad) {
     int rc = validate(p, grad);
     if (rc != PML_OK) return rc;
+    DeviceGuard guard(p->target);
+    if (guard.foreign(p->pass[0].disp) || guard.foreign(p->losses) || guard.foreign(p->sources[0]) || guard.foreign(ws))
+        return PML_ERR_INVALID;   // tensors of one call must live on one device
     Plan pl = make_plan(p, grad);
     if (!ws || ws_bytes < pl.total) return PML_ERR_WORKSPACE;
     if ((reinterpret_cast<uintptr_t>(ws) & 15) != 0) return PML_ERR_INVALID;
@@ -245,6 +295,11 @@ int run_loss(const pml_problem* p, void* ws, size_t ws_bytes, cudaStream_t st, b
 
     // 1-2. smoothness term (writes grad_disp first; the photometric kernel adds onto it)
     SmoothParams sp;
+    const pml_segments* sg = p->segments;
+    sp.n_seg = sg ? sg->n_seg : 0; sp.seg_size = sg ? sg->seg_size : 0;
+    if (sg)
+        for (int i = 0; i < p->n_pass; ++i)
+            for (int j = 0; j < sg->n_seg; ++j) sp.color_c[i].p[j] = sg->smooth_color[i][j];
     sp.B = p->B; sp.n_pass = p->n_pass; sp.disp_mean = mean; sp.part = spart;
     sp.mean_part = meanpart; sp.max_chunks = pl.max_chunks;
     for (int i = 0; i < p->n_pass; ++i) {
@@ -273,11 +328,17 @@ int run_loss(const pml_problem* p, void* ws, size_t ws_bytes, cudaStream_t st, b
             IdentityParams ip;
             const int pair_n = (fa + 1 < p->S) ? 2 : 1;
             ip.target = p->target; ip.src0 = p->sources[fa]; ip.src1 = p->sources[fa + pair_n - 1];
+            ip.n_seg = sp.n_seg; ip.seg_size = sp.seg_size;
+            if (sg)
+                for (int j = 0; j < sg->n_seg; ++j) {
+                    ip.target_c.p[j] = sg->target[j]; ip.src0_c.p[j] = sg->sources[fa][j];
+                    ip.src1_c.p[j] = sg->sources[fa + pair_n - 1][j];
+                }
             ip.out = identity; ip.B = p->B; ip.H = p->H; ip.W = p->W; ip.S = pair_n;
             ip.avg = (p->flags & PML_FLAG_AVG_REPROJ) ? 1 : 0;
             ip.n_out = pl.n_id; ip.plane_off = ip.avg ? 0 : fa; ip.accumulate = (ip.avg && fa > 0) ? 1 : 0;
             ip.inv_total = 1.0f / (float)p->S;
-            ip.TH = env_int("PML_ID_TH", 16);
+            ip.TH = knobs().id_th;
             ip.n_strips = (p->W + kPrepTW - 1) / kPrepTW;
             ip.n_chunks = (p->H + ip.TH - 1) / ip.TH;
             const dim3 g(ip.n_chunks * ip.n_strips, p->B);
@@ -325,6 +386,12 @@ int run_loss(const pml_problem* p, void* ws, size_t ws_bytes, cudaStream_t st, b
     pp.mode = 0; pp.f_base = 0; pp.pair_n = p->S > 1 ? 2 : 1; pp.rp = nullptr;
     pp.cta_per_pass = pl.cta_per_pass; pp.part = part; pp.part_stride = pl.part_stride;
     pp.inv_n = (float)(1.0 / ((double)p->B * p->H * p->W));
+    pp.n_seg = sp.n_seg; pp.seg_size = sp.seg_size;
+    if (sg)
+        for (int j = 0; j < sg->n_seg; ++j) {
+            pp.target_c.p[j] = sg->target[j]; pp.K_c.p[j] = sg->K[j]; pp.invK_c.p[j] = sg->inv_K[j];
+            for (int f = 0; f < p->S; ++f) pp.src_c[f].p[j] = sg->sources[f][j];
+        }
     if (p->prof_start) pml_event_record(p->prof_start, st);
     if (pl.two_sweeps) {
         // More than two source frames (or per-frame weights): (1) forward sweep per frame pair -> reprojection losses,
@@ -367,15 +434,18 @@ int run_loss(const pml_problem* p, void* ws, size_t ws_bytes, cudaStream_t st, b
     fq.B = p->B; fq.S = p->S; fq.n_pass = p->n_pass; fq.cta_per_pass = pl.cta_per_pass;
     fq.cta_per_image = pl.n_chunks * pl.n_strips; fq.part_stride = pl.part_stride; fq.with_grad = grad ? 1 : 0;
     fq.inv_n = pp.inv_n;
+    fq.n_seg = sp.n_seg; fq.seg_size = sp.seg_size;
+    if (sg) for (int j = 0; j < sg->n_seg; ++j) fq.K_c.p[j] = sg->K[j];
     fq.part = part; fq.K = p->K; fq.smooth_part = spart; fq.disp_mean = mean;
     for (int i = 0; i < p->n_pass; ++i) {
         fq.smooth_blocks[i] = pl.smooth_blocks[i]; fq.smooth_off[i] = pl.smooth_off[i];
         fq.hd[i] = p->pass[i].hd; fq.wd[i] = p->pass[i].wd; fq.smooth_weight[i] = p->pass[i].smooth_weight;
     }
     fq.losses = p->losses; fq.loss_vector = p->loss_vector; fq.grad_T = p->grad_T; fq.grad_disp_const = p->grad_disp_const;
+    fq.loss_total = p->loss_total; fq.total_div = p->loss_total_div > 0.f ? p->loss_total_div : (float)p->n_pass;
     fq.image_part = imagepart;
     PML_LAUNCH(finalize_image_kernel, dim3(p->B, p->n_pass), dim3(256), 0, st, fq);
-    PML_LAUNCH(finalize_loss_kernel, dim3(p->n_pass), dim3(32), 0, st, fq);
+    PML_LAUNCH(finalize_loss_kernel, dim3(1), dim3(32), 0, st, fq);
     return cudaGetLastError() == cudaSuccess ? PML_OK : PML_ERR_CUDA;
 }
 
@@ -412,9 +482,11 @@ int pml_loss_forward_backward(const pml_problem* p, void* ws, size_t ws_bytes, p
 
 int pml_scale_grads(int32_t n_pass, int32_t B, int32_t S, const int32_t* hd, const int32_t* wd,
                     float* const* grad_disp, const float* grad_disp_const, const float* grad_T,
-                    const float* upstream, float* grad_T_out, pml_stream_t stream) {
+                    const float* upstream, const float* upstream_total, float total_div,
+                    float* grad_T_out, pml_stream_t stream) {
     if (n_pass < 1 || n_pass > PML_MAX_PASSES || B < 1 || S < 1 || S > PML_MAX_SOURCES) return PML_ERR_INVALID;
-    if (!hd || !wd || !grad_disp || !grad_disp_const || !grad_T || !upstream || !grad_T_out) return PML_ERR_INVALID;
+    if (!hd || !wd || !grad_disp || !grad_disp_const || !grad_T || (!upstream && !upstream_total) || !grad_T_out) return PML_ERR_INVALID;
+    DeviceGuard guard(grad_T);
     pml::ScaleParams sp;
     sp.n_pass = n_pass; sp.B = B; sp.S = S;
     long long total = 0;
@@ -425,7 +497,8 @@ int pml_scale_grads(int32_t n_pass, int32_t B, int32_t S, const int32_t* hd, con
         total += (long long)B * hd[i] * wd[i];
     }
     sp.off[n_pass] = total;
-    sp.gconst = grad_disp_const; sp.gT = grad_T; sp.up = upstream; sp.gT_out = grad_T_out;
+    sp.gconst = grad_disp_const; sp.gT = grad_T; sp.up = upstream; sp.up_total = upstream_total;
+    sp.inv_div = 1.0f / (total_div > 0.f ? total_div : (float)n_pass); sp.gT_out = grad_T_out;
     int max_n = 1;
     for (int i = 0; i < n_pass; ++i) if (sp.per_image[i] > max_n) max_n = sp.per_image[i];
     int chunks = (max_n + pml::kScaleChunk - 1) / pml::kScaleChunk;
@@ -433,6 +506,22 @@ int pml_scale_grads(int32_t n_pass, int32_t B, int32_t S, const int32_t* hd, con
     while (chunks * B < pose_blocks) ++chunks;
     if (B > 65535) return PML_ERR_UNSUPPORTED;
     PML_LAUNCH(pml::scale_grads_kernel, dim3(chunks, B, n_pass + 1), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), sp);
+    return cudaGetLastError() == cudaSuccess ? PML_OK : PML_ERR_CUDA;
+}
+
+int pml_selection_masks(int32_t n_pass, int64_t n_pix, const uint8_t* const* argmin, int32_t n_id,
+                        float* const* out, pml_stream_t stream) {
+    if (n_pass < 1 || n_pass > PML_MAX_PASSES || n_pix < 1 || n_id < 1 || !argmin || !out) return PML_ERR_INVALID;
+    pml::SelectionParams q;
+    for (int i = 0; i < n_pass; ++i) {
+        if (!argmin[i] || !out[i]) return PML_ERR_INVALID;
+        q.argmin[i] = argmin[i]; q.out[i] = out[i];
+    }
+    q.n_pix = n_pix; q.n_id = n_id;
+    DeviceGuard guard(out[0]);
+    const long long per_block = 256LL * 16;
+    PML_LAUNCH(pml::selection_mask_kernel, dim3((unsigned)((n_pix + per_block - 1) / per_block), n_pass), dim3(256), 0,
+               reinterpret_cast<cudaStream_t>(stream), q);
     return cudaGetLastError() == cudaSuccess ? PML_OK : PML_ERR_CUDA;
 }
 

@@ -20,6 +20,17 @@ constexpr float kSsimC1 = 0.0001f;   // 0.01^2, layers.py:231
 constexpr float kSsimC2 = 0.0009f;   // 0.03^2, layers.py:232
 constexpr float kTieNoise = 0.00001f;  // trainer.py:595
 
+// A batch that arrives as n_seg separately allocated chunks of seg_size images (pml_segments: the per-timestep
+// tensors of trainer_gru.py:890-899,943-957).  n_seg == 0: one tensor over the whole batch.
+struct ChunkPtrs { const float* p[PML_MAX_SEGMENTS]; };
+// base pointer of the tensor that holds image b, and b's index inside it
+__device__ __forceinline__ const float* chunk_of(const float* whole, const ChunkPtrs& c, int n_seg, int seg_size, int b, int& local) {
+    if (n_seg <= 0) { local = b; return whole; }
+    const int sb = b / seg_size;
+    local = b - sb * seg_size;
+    return c.p[sb];
+}
+
 // ReflectionPad2d(1) index map restricted to the one-pixel ring (layers.py:229): -1 -> 1, n -> n-2.
 __device__ __forceinline__ int reflect1(int i, int n) {
     i = i < 0 ? -i : i;
@@ -36,7 +47,13 @@ __device__ __forceinline__ float warp_sum(float v) {
 // One SSIM window (layers.py:238-248) from its five 3x3 sums.  Returns the dissimilarity
 // clamp((1 - n/d)/2, 0, 1); if WITH_GRAD also the partials of that value with respect to the
 // three x-dependent *sums* (Sx, Sxx, Sxy), zero where the clamp is active.
-template <bool WITH_GRAD>
+//
+// LOWER_GATE: the reference clamps at 0 and 1 (layers.py:248) and autograd zeroes the gradient outside.
+// In exact arithmetic n/d <= 1 always (2 mu_x mu_y <= mu_x^2 + mu_y^2, 2 sigma_xy <= sigma_x + sigma_y), so
+// the clamp at 0 can only trigger through fp32 round-off on windows where x ~ y; the layer-level drop-in
+// keeps ATen's behaviour bit for bit (LOWER_GATE), the fused loss follows the mathematical function -- and
+// the float64 reference -- and lets the (tiny) gradient through there.
+template <bool WITH_GRAD, bool LOWER_GATE = true>
 __device__ __forceinline__ float ssim_window(float Sx, float Sy, float Sxx, float Syy, float Sxy,
                                              float& dSx, float& dSxx, float& dSxy) {
     const float k9 = 1.0f / 9.0f;
@@ -60,7 +77,7 @@ __device__ __forceinline__ float ssim_window(float Sx, float Sy, float Sxx, floa
     float val = fminf(fmaxf(raw, 0.0f), 1.0f);
     if (WITH_GRAD) {
         // clamp backward passes the gradient on the closed interval [0,1]
-        float gate = (raw >= 0.0f && raw <= 1.0f) ? 1.0f : 0.0f;
+        float gate = ((!LOWER_GATE || raw >= 0.0f) && raw <= 1.0f) ? 1.0f : 0.0f;
         float dA1 = -0.5f * A2 * inv;
         float dA2 = -0.5f * A1 * inv;
         float dB1 = 0.5f * ratio * (inv * B2);  // ratio / B1

@@ -15,9 +15,14 @@ struct ScaleParams {
     long long off[PML_MAX_PASSES + 1];
     const float* gconst;   // [n_pass][B]
     const float* gT;       // [n_pass][S][B][16]
-    const float* up;       // [n_pass]
+    const float* up;       // [n_pass] gradient arriving at the per-scale losses, or null
+    const float* up_total; // [1] gradient arriving at the total (mean over scales), or null
+    float inv_div;         // 1 / divisor of the total
     float* gT_out;         // [S][B][16]
 };
+__device__ __forceinline__ float scale_upstream(const ScaleParams& q, int k) {
+    return (q.up ? __ldg(q.up + k) : 0.f) + (q.up_total ? __ldg(q.up_total) * q.inv_div : 0.f);
+}
 
 // grid = (chunks, B, n_pass + 1): planes z < n_pass scale one image of one scale (float4 where the
 // image size allows), plane z == n_pass reduces the pose gradients over the scales.
@@ -30,7 +35,7 @@ scale_grads_kernel(const ScaleParams q) {
         if (e < q.S * q.B * 16) {
             float acc = 0.f;
             for (int k = 0; k < q.n_pass; ++k)
-                acc = fmaf(q.up[k], q.gT[(size_t)k * q.S * q.B * 16 + e], acc);
+                acc = fmaf(scale_upstream(q, k), q.gT[(size_t)k * q.S * q.B * 16 + e], acc);
             q.gT_out[e] = acc;
         }
         return;
@@ -38,7 +43,7 @@ scale_grads_kernel(const ScaleParams q) {
     const int n = q.per_image[pi];
     const int base = blockIdx.x * kScaleChunk;
     if (base >= n) return;
-    const float up = __ldg(q.up + pi), c = __ldg(q.gconst + pi * q.B + b);
+    const float up = scale_upstream(q, pi), c = __ldg(q.gconst + pi * q.B + b);
     float* g = q.g[pi] + (size_t)b * n;
     if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0) {
 #pragma unroll
@@ -52,6 +57,38 @@ scale_grads_kernel(const ScaleParams q) {
         }
     } else {
         for (int i = base + threadIdx.x; i < min(base + kScaleChunk, n); i += 256) g[i] = up * (g[i] + c);
+    }
+}
+
+// ---------------------------------------------------------------- identity_selection (trainer.py:606-608)
+struct SelectionParams {
+    const uint8_t* argmin[PML_MAX_PASSES];
+    float* out[PML_MAX_PASSES];
+    long long n_pix;
+    int n_id;
+};
+// grid = (chunks, n_pass); 16 pixels per thread where the pointers allow (uint4 in, 4 x float4 out)
+__global__ void __launch_bounds__(256)
+selection_mask_kernel(const SelectionParams q) {
+    const uint8_t* a = q.argmin[blockIdx.y];
+    float* o = q.out[blockIdx.y];
+    const long long i0 = ((long long)blockIdx.x * 256 + threadIdx.x) * 16;
+    if (i0 >= q.n_pix) return;
+    const unsigned thr = (unsigned)(q.n_id - 1);   // idx > n_id - 1 (trainer.py:607); the caller guarantees n_id >= 1
+    if (i0 + 16 <= q.n_pix && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(o)) & 15) == 0) {
+        const uint4 v = *reinterpret_cast<const uint4*>(a + i0);
+        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float4 r;
+            r.x = ((w[k] & 0xffu) > thr) ? 1.f : 0.f;
+            r.y = (((w[k] >> 8) & 0xffu) > thr) ? 1.f : 0.f;
+            r.z = (((w[k] >> 16) & 0xffu) > thr) ? 1.f : 0.f;
+            r.w = ((w[k] >> 24) > thr) ? 1.f : 0.f;
+            *reinterpret_cast<float4*>(o + i0 + 4 * k) = r;
+        }
+    } else {
+        for (long long i = i0; i < min(i0 + 16, q.n_pix); ++i) o[i] = ((unsigned)a[i] > thr) ? 1.f : 0.f;
     }
 }
 

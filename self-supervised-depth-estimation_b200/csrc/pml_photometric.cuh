@@ -57,6 +57,9 @@ struct PhotoParams {
     float* part;      // [n_cta][part_stride]: loss partial, then S x 12 dL/dP partials
     int part_stride;
     float inv_n;      // 1 / (B*H*W)
+    // chunked batch (pml_segments), honoured by the warp-strip sweep only
+    int n_seg, seg_size;
+    ChunkPtrs target_c, K_c, invK_c, src_c[PML_MAX_SOURCES];
 };
 
 constexpr int kGeoFields = 13;  // per frame in the row ring: x[3] dpx[3] dpy[3] invz u v wgt
@@ -371,7 +374,7 @@ photometric_kernel(const PhotoParams p) {
                     const float Sy = hy2[c] + hy1[c] + hyn[c];
                     const float Syy = hyy2[c] + hyy1[c] + hyyn[c];
                     float dSx = 0.f, dSxx = 0.f, dSxy = 0.f;
-                    ssim_sum += ssim_window<GRAD>(Sx, Sy, Sxx, Syy, Sxy, dSx, dSxx, dSxy);
+                    ssim_sum += ssim_window<GRAD, false>(Sx, Sy, Sxx, Syy, Sxy, dSx, dSxx, dSxy);
                     if (GRAD) {
                         // d rp / d x_q = kssim * (dSx + 2 x_q dSxx + y_q dSxy) for q in the window
                         coef[f][c] = kssim * dSx;
@@ -613,8 +616,12 @@ struct FinalizeParams {
     float* image_part;         // [n_pass][B][4]: photometric sum, smooth x sum, smooth y sum, -
     float* losses;             // [n_pass][4]
     float* loss_vector;        // [n_pass] or null: loss_s once more, contiguous
+    float* loss_total;         // [1] or null: sum_s loss_s / total_div (trainer.py:618-621)
+    float total_div;
     float* grad_T;             // [n_pass][S][B][16]
     float* grad_disp_const;    // [n_pass][B]
+    int n_seg, seg_size;
+    ChunkPtrs K_c;
 };
 
 __global__ void __launch_bounds__(256)
@@ -668,30 +675,43 @@ finalize_image_kernel(const FinalizeParams q) {
     // dL/dT = K[:3,:]^T dL/dP  (layers.py:183: P = (K T)[:3])
     if (q.with_grad && tid < q.S * 16) {
         const int f = tid >> 4, e = tid & 15, kk = e >> 2, j = e & 3;
-        const float* Kb = q.K + (size_t)b * 16;
+        int bl;
+        const float* Kb = chunk_of(q.K, q.K_c, q.n_seg, q.seg_size, b, bl) + (size_t)bl * 16;
         const float* gp = s_col + 1 + f * 12;
         q.grad_T[((size_t)(pi * q.S + f) * q.B + b) * 16 + e] =
             fmaf(Kb[kk], gp[j], fmaf(Kb[4 + kk], gp[4 + j], Kb[8 + kk] * gp[8 + j]));
     }
 }
 
+// one warp: lane pi reduces scale pi over the images (fixed order), lane 0 then adds the scales in
+// order like `total_loss += loss; total_loss /= num_scales` (trainer.py:618-621)
 __global__ void __launch_bounds__(32)
 finalize_loss_kernel(const FinalizeParams q) {
-    const int pi = blockIdx.x;
-    if (threadIdx.x != 0) return;
-    float ph = 0.f, sx = 0.f, sy = 0.f;
-    for (int b = 0; b < q.B; ++b) {
-        const float* ip = q.image_part + (size_t)(pi * q.B + b) * 4;
-        ph += ip[0]; sx += ip[1]; sy += ip[2];
+    __shared__ float s_loss[PML_MAX_PASSES];
+    const int pi = threadIdx.x;
+    if (pi < q.n_pass) {
+        double ph = 0.0, sx = 0.0, sy = 0.0;   // a handful of adds per launch: double costs nothing here
+        for (int b = 0; b < q.B; ++b) {
+            const float* ip = q.image_part + (size_t)(pi * q.B + b) * 4;
+            ph += (double)ip[0]; sx += (double)ip[1]; sy += (double)ip[2];
+        }
+        const float h = (float)q.hd[pi], w = (float)q.wd[pi];
+        const float photo = (float)(ph * (double)q.inv_n);
+        const float sm = (float)sx / ((float)q.B * h * (w - 1.f)) + (float)sy / ((float)q.B * (h - 1.f) * w);   // layers.py:215
+        const float loss = photo + q.smooth_weight[pi] * sm;   // trainer.py:610,616
+        q.losses[pi * 4 + 0] = loss;
+        q.losses[pi * 4 + 1] = photo;
+        q.losses[pi * 4 + 2] = sm;
+        q.losses[pi * 4 + 3] = 0.f;
+        if (q.loss_vector != nullptr) q.loss_vector[pi] = loss;
+        s_loss[pi] = loss;
     }
-    const float h = (float)q.hd[pi], w = (float)q.wd[pi];
-    const float photo = ph * q.inv_n;
-    const float sm = sx / ((float)q.B * h * (w - 1.f)) + sy / ((float)q.B * (h - 1.f) * w);   // layers.py:215
-    q.losses[pi * 4 + 0] = photo + q.smooth_weight[pi] * sm;   // trainer.py:610,616
-    q.losses[pi * 4 + 1] = photo;
-    q.losses[pi * 4 + 2] = sm;
-    q.losses[pi * 4 + 3] = 0.f;
-    if (q.loss_vector != nullptr) q.loss_vector[pi] = photo + q.smooth_weight[pi] * sm;
+    __syncwarp();
+    if (pi == 0 && q.loss_total != nullptr) {
+        float t = 0.f;
+        for (int k = 0; k < q.n_pass; ++k) t += s_loss[k];
+        q.loss_total[0] = t / q.total_div;
+    }
 }
 
 }  // namespace pml

@@ -50,6 +50,8 @@ struct IdentityParams {
     int accumulate;        // avg: add to what an earlier pair wrote
     float inv_total;       // avg: 1 / total source frames
     int TH, n_strips, n_chunks;
+    int n_seg, seg_size;   // chunked batch (pml_segments)
+    ChunkPtrs target_c, src0_c, src1_c;
 };
 
 // one warp = one (chunk, strip) item `bx` of image `b`
@@ -63,7 +65,11 @@ __device__ __forceinline__ void identity_sweep_body(const IdentityParams& p, con
     const int cx = x0 - 1 + lane;
     const int rx = reflect1(clampi(cx, -1, W), W);
     const bool owned = (cx >= x0) && (cx < x1);
-    const int b3p = b * 3 * plane;
+    int bl;
+    const float* __restrict__ tgt_g = chunk_of(p.target, p.target_c, p.n_seg, p.seg_size, b, bl);
+    const float* __restrict__ s0_g = chunk_of(p.src0, p.src0_c, p.n_seg, p.seg_size, b, bl);
+    const float* __restrict__ s1_g = chunk_of(p.src1, p.src1_c, p.n_seg, p.seg_size, b, bl);
+    const int b3p = bl * 3 * plane;
     float* out_b = p.out + ((size_t)b * p.n_out + p.plane_off) * plane;
 
     float hy1[3], hy2[3], hyy1[3], hyy2[3];
@@ -83,8 +89,8 @@ __device__ __forceinline__ void identity_sweep_body(const IdentityParams& p, con
         const int o = b3p + ry * W + rx;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            row.y[c] = __ldg(at(p.target, o + c * plane));
-            row.x[c] = f2(__ldg(at(p.src0, o + c * plane)), __ldg(at(p.src1, o + c * plane)));
+            row.y[c] = __ldg(at(tgt_g, o + c * plane));
+            row.x[c] = f2(__ldg(at(s0_g, o + c * plane)), __ldg(at(s1_g, o + c * plane)));
         }
     };
     auto step = [&](const int r, const Row& row, float (&hyA)[3], float (&hyB)[3], float (&hyyA)[3], float (&hyyB)[3],
@@ -188,7 +194,8 @@ __device__ __forceinline__ void smooth_sweep_body(const SmoothParams& q, const i
     const float nx_ = 1.0f / ((float)q.B * (float)h * (float)(w - 1));
     const float ny_ = 1.0f / ((float)q.B * (float)(h - 1) * (float)w);
     const float* dg = ps.disp + (size_t)b * n;
-    const float* cg = ps.color + (size_t)b * 3 * n;
+    int bl;
+    const float* cg = chunk_of(ps.color, q.color_c[pi], q.n_seg, q.seg_size, b, bl) + (size_t)bl * 3 * n;
 
     float ex = 0.f, ey = 0.f, gd = 0.f;
     // previous row (y-1): normalised disparity, raw disparity, colours, its horizontal adjoint, and

@@ -20,6 +20,8 @@ struct SmoothParams {
     float* mean_part;     // [n_pass][B][max_chunks] partial sums of disp (4096 px each)
     int max_chunks;
     float* part;          // [total_blocks][3]
+    int n_seg, seg_size;  // chunked batch (pml_segments): colour of pass i, chunk j = color_c[i].p[j]
+    ChunkPtrs color_c[PML_MAX_PASSES];
 };
 
 // per-image mean of the disparity (trainer.py:612), two stages: 4096-pixel partial sums here,
@@ -85,7 +87,8 @@ smooth_kernel(const SmoothParams q) {
     if (idx < n) {
         const int y = idx / w, x = idx - y * w;
         const float* d = ps.disp + (size_t)b * n;
-        const float* img = ps.color + (size_t)b * 3 * n;
+        int bl;
+        const float* img = chunk_of(ps.color, q.color_c[pi], q.n_seg, q.seg_size, b, bl) + (size_t)bl * 3 * n;
         const float inv = __fdiv_rn(1.0f, s_mean + 1e-7f);
         const float nx_ = 1.0f / ((float)q.B * (float)h * (float)(w - 1));
         const float ny_ = 1.0f / ((float)q.B * (float)(h - 1) * (float)w);

@@ -104,8 +104,9 @@ __device__ __forceinline__ float2 ssim_pair(float2 Sx, float2 Sxx, float2 Sxy, f
     const float2 ratio = mul2(num, q);
     const float2 val = f2(__saturatef(fmaf(-0.5f, ratio.x, 0.5f)), __saturatef(fmaf(-0.5f, ratio.y, 0.5f)));
     if (WITH_GRAD) {
-        // clamp backward passes the gradient on the closed interval: 0 <= raw <= 1  <=>  |ratio| <= 1
-        const float2 gq = f2(fabsf(ratio.x) <= 1.0f ? q.x : 0.f, fabsf(ratio.y) <= 1.0f ? q.y : 0.f);
+        // clamp backward (layers.py:248) zeroes the gradient where raw > 1  <=>  ratio < -1.  The clamp at 0
+        // (ratio > 1) cannot trigger in exact arithmetic (see ssim_window): it is left open, like float64
+        const float2 gq = f2(ratio.x >= -1.0f ? q.x : 0.f, ratio.y >= -1.0f ? q.y : 0.f);
         pe = mul2(f2(-gq.x, -gq.y), A1);                         // d/dSxy * 9
         pb = mul2(mul2(gq, ratio), B1);                          // 2 * d/dSxx * 9
         const float2 w = mul2(mul2(mx, ratio), sub2(B2, B1));
@@ -185,18 +186,31 @@ sweep_kernel(const PhotoParams p) {
     float* sG = wsm + 48;                                  // [32] staging row of the transposed upsample
     float4* sRing = reinterpret_cast<float4*>(wsm + 80);   // [kSweepRingSlots][kSweepRingQ][32]
 
+    // chunked batch (pml_segments): image b is image `bl` of the tensors of chunk b / seg_size
+    int bl = b;
+    const float* __restrict__ tgt_g = p.target;
+    const float* __restrict__ src0_g = p.src[fa];
+    const float* __restrict__ src1_g = p.src[fb];
+    const float* K_g = p.K;
+    const float* iK_g = p.invK;
+    if (p.n_seg > 0) {
+        const int sb = b / p.seg_size;
+        bl = b - sb * p.seg_size;
+        tgt_g = p.target_c.p[sb]; src0_g = p.src_c[fa].p[sb]; src1_g = p.src_c[fb].p[sb];
+        K_g = p.K_c.p[sb]; iK_g = p.invK_c.p[sb];
+    }
     float rc0, rc1, rc2;    // column part of the back-projection ray r = inv_K[:3,:3] @ (x, y, 1)
     {
         if (lane < 24) {
             const int e = lane >> 1, f = (lane & 1) ? fb : fa, i = e >> 2, j = e & 3;
-            const float* Kb = p.K + b * 16;
+            const float* Kb = K_g + bl * 16;
             const float* Tb = p.T[f] + b * 16;
             float a = 0.f;
 #pragma unroll
             for (int k = 0; k < 4; ++k) a = fmaf(Kb[i * 4 + k], Tb[k * 4 + j], a);   // layers.py:183
             wsm[lane] = a;
         }
-        const float* ikb = p.invK + b * 16;                                          // layers.py:164
+        const float* ikb = iK_g + bl * 16;                                           // layers.py:164
         if (lane == 0) {
             wsm[24] = ikb[1]; wsm[25] = ikb[2]; wsm[26] = ikb[5]; wsm[27] = ikb[6];
             wsm[28] = ikb[9]; wsm[29] = ikb[10]; wsm[30] = 0.f; wsm[31] = 0.f;
@@ -221,15 +235,12 @@ sweep_kernel(const PhotoParams p) {
     const int plane = H * W;
     // All global addressing is `parameter pointer [32-bit element index]`: every tensor of a call has
     // fewer than 2^31 elements (checked on the host).
-    const float* __restrict__ tgt_g = p.target;
-    const float* __restrict__ src0_g = p.src[fa];
-    const float* __restrict__ src1_g = p.src[fb];
     const float* __restrict__ disp_g = ps.disp;
     const float* __restrict__ id_g = p.identity;
     const float* __restrict__ nz_g = COMMON ? nullptr : ps.noise;
     const float* __restrict__ fw_g = COMMON ? nullptr : ps.fw;      // predictive mask and its gradient
     float* __restrict__ gfw_g = COMMON ? nullptr : ps.gfw;
-    const int b3p = b * 3 * plane;          // image offset in a [B,3,H,W] tensor
+    const int b3p = bl * 3 * plane;         // image offset in a [B,3,H,W] input tensor (of its chunk)
     const int bdp = b * hd * wd;            // ... in disp_s / grad_disp_s
     const int bip = b * n_id * plane;       // ... in the identity-loss / noise tensors
     const int bp = b * plane;               // ... in a [B,1,H,W] tensor
@@ -489,8 +500,8 @@ sweep_kernel(const PhotoParams p) {
             if (ps.warped != nullptr) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    ps.warped[(size_t)fa * p.B * 3 * plane + b3p + c * plane + o] = xv[c].x;
-                    if (two) ps.warped[(size_t)fb * p.B * 3 * plane + b3p + c * plane + o] = xv[c].y;
+                    ps.warped[(size_t)fa * p.B * 3 * plane + 3 * bp + c * plane + o] = xv[c].x;
+                    if (two) ps.warped[(size_t)fb * p.B * 3 * plane + 3 * bp + c * plane + o] = xv[c].y;
                 }
             }
         }

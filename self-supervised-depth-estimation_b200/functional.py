@@ -16,7 +16,7 @@ from typing import Dict, List, Optional, Sequence
 import torch
 
 from . import _cabi
-from ._cabi import (PML_FLAG_AVG_REPROJ, PML_FLAG_NO_AUTOMASK, PML_FLAG_NO_SSIM, PML_MAX_PASSES,
+from ._cabi import (PML_FLAG_AVG_REPROJ, PML_FLAG_KERNEL_CTA, PML_FLAG_NO_AUTOMASK, PML_FLAG_NO_SSIM, PML_MAX_PASSES,
                     PML_MAX_SOURCES, PmlProblem, get_library)
 
 
@@ -40,85 +40,185 @@ def _ptr(t: Optional[torch.Tensor]):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
 
+class _Plan:
+    """Launch state of one problem configuration that survives from step to step: the pml_problem with its
+    static fields filled, the workspace (re-used: every call is stream-ordered on the stream the plan was
+    made for), the ctypes arrays of the backward.  Keyed by shapes, flags and stream in ``_PLANS``."""
+    __slots__ = ("prob", "ws", "ws_bytes", "hd", "wd", "gptrs", "shapes", "gdisp_off", "gdisp_total", "small_off",
+                 "small_total", "n_id", "segs")
+
+
+_PLANS: Dict = {}
+_PLANS_MAX = 64
+
+
+def _tensor_list(x):
+    return list(x) if isinstance(x, (list, tuple)) else None
+
+
+def _make_plan(lib, cfg, target0, disps, dev, n_seg, seg_size):
+    n_pass, S = cfg["n_pass"], cfg["S"]
+    _, _, H, W = target0.shape
+    B = disps[0].shape[0]
+    pl = _Plan()
+    prob = PmlProblem()
+    prob.B, prob.H, prob.W, prob.S, prob.n_pass = B, H, W, S, n_pass
+    prob.flags = cfg["flags"]
+    prob.min_depth, prob.max_depth, prob.eps = cfg["min_depth"], cfg["max_depth"], cfg.get("eps", 1e-7)
+    prob.loss_total_div = float(cfg.get("total_div") or n_pass)
+    automask = not (cfg["flags"] & PML_FLAG_NO_AUTOMASK)
+    pl.n_id = 0 if not automask else (1 if cfg["flags"] & PML_FLAG_AVG_REPROJ else S)
+    pl.shapes = [(d.shape[2], d.shape[3]) for d in disps]
+    off = 0
+    pl.gdisp_off = []
+    for i, (hd, wd) in enumerate(pl.shapes):
+        ps = prob.passes[i]
+        ps.hd, ps.wd = hd, wd
+        ps.smooth_weight = cfg["smooth_weights"][i]
+        pl.gdisp_off.append(off)
+        off += (B * hd * wd + 3) // 4 * 4          # keep every slice 16-byte aligned
+    pl.gdisp_total = off
+    # one fp32 arena per call: terms [n_pass,4] | loss vector [n_pass] | total [1] | pad | grad_const [n_pass,B] | grad_T [n_pass,S,B,16]
+    so = {"terms": 0, "vec": 4 * n_pass, "total": 5 * n_pass}
+    o = (5 * n_pass + 1 + 3) // 4 * 4
+    so["gconst"] = o
+    o = (o + n_pass * B + 3) // 4 * 4
+    so["gT"] = o
+    pl.small_off, pl.small_total = so, o + n_pass * S * B * 16
+    pl.segs = None
+    if n_seg:
+        pl.segs = _cabi.PmlSegments()
+        pl.segs.n_seg, pl.segs.seg_size = n_seg, seg_size
+        prob.segments = ctypes.pointer(pl.segs)
+    pl.hd = (ctypes.c_int32 * n_pass)(*[s_[0] for s_ in pl.shapes])
+    pl.wd = (ctypes.c_int32 * n_pass)(*[s_[1] for s_ in pl.shapes])
+    pl.gptrs = (ctypes.c_void_p * n_pass)()
+    pl.prob = prob
+    pl.ws = None
+    pl.ws_bytes = -1
+    return pl
+
+
 class _PhotometricLoss(torch.autograd.Function):
-    """inputs: cfg, then tensors laid out as
-    disps[n_pass] | Ts[S] | frame_weights[n_pass or 0] | target | K | inv_K | sources[S] |
-    smooth_colors[n_pass] | noise[n_pass or 0]"""
+    """inputs: cfg (carries the tensors that never receive gradients: images, intrinsics, noise), then the
+    differentiable tensors laid out as  disps[n_pass] | Ts[S] | frame_weights[n_pass or 0]"""
 
     @staticmethod
     def forward(ctx, cfg: Dict, *tensors):
         lib = get_library()
         n_pass, S = cfg["n_pass"], cfg["S"]
+        has_fw = bool(cfg.get("has_fw"))
         tensors = [_check(t, "tensor[%d]" % i, lib) for i, t in enumerate(tensors)]
-        it = iter(tensors)
-        disps = [next(it) for _ in range(n_pass)]
-        Ts = [next(it) for _ in range(S)]
-        fws = [next(it) for _ in range(n_pass)] if cfg.get("has_fw") else [None] * n_pass
-        n_diff = n_pass + S + (n_pass if cfg.get("has_fw") else 0)
-        target, K, inv_K = next(it), next(it), next(it)
-        sources = [next(it) for _ in range(S)]
-        colors = [next(it) for _ in range(n_pass)]
-        noise = [next(it) for _ in range(n_pass)] if cfg["has_noise"] else [None] * n_pass
+        disps = tensors[:n_pass]
+        Ts = tensors[n_pass:n_pass + S]
+        fws = tensors[n_pass + S:] if has_fw else [None] * n_pass
+        img = cfg["images"]
+        n_seg = img["n_seg"]
 
-        B, C, H, W = target.shape
+        def chk(x, name):
+            if n_seg:
+                return [_check(t, name, lib) for t in x]
+            return _check(x, name, lib)
+        target, K, inv_K = chk(img["target"], "target"), chk(img["K"], "K"), chk(img["inv_K"], "inv_K")
+        sources = [chk(x, "source") for x in img["sources"]]
+        colors = [chk(x, "smooth colour") for x in img["colors"]]
+        noise = [_check(t, "noise", lib) for t in img["noise"]] if cfg["has_noise"] else [None] * n_pass
+        target0 = target[0] if n_seg else target
+        seg_size = target0.shape[0] if n_seg else 0
+        B = disps[0].shape[0]
+        _, C, H, W = target0.shape
         if C != 3:
             raise ValueError("target must be [B,3,H,W]")
-        need = ctx.needs_input_grad[1:]
-        if any(need[n_diff:]):
-            raise NotImplementedError(
-                "gradients with respect to images / intrinsics / noise are not produced by libpml "
-                "(the reference never requests them: colour inputs carry no grad, trainer.py:233-237)")
-        want_grad = any(need[:n_diff])
-        dev = target.device
-        f32 = dict(device=dev, dtype=torch.float32)
+        if (seg_size * n_seg if n_seg else target0.shape[0]) != B:
+            raise ValueError("images and disparities disagree on the batch size")
+        want_grad = any(ctx.needs_input_grad[1:])
+        dev = target0.device
+        stream = torch.cuda.current_stream(dev).cuda_stream if target0.is_cuda else 0
 
-        prob = PmlProblem()
-        prob.B, prob.H, prob.W, prob.S, prob.n_pass = B, H, W, S, n_pass
-        prob.flags = cfg["flags"]
-        prob.min_depth, prob.max_depth, prob.eps = cfg["min_depth"], cfg["max_depth"], cfg.get("eps", 1e-7)
+        key = (dev, stream, B, H, W, S, n_pass, cfg["flags"], tuple(d.shape[2:] for d in disps), cfg["min_depth"],
+               cfg["max_depth"], tuple(cfg["smooth_weights"]), cfg.get("total_div"), n_seg, seg_size)
+        pl = _PLANS.get(key)
+        if pl is None:
+            if len(_PLANS) >= _PLANS_MAX:
+                _PLANS.clear()
+            pl = _PLANS[key] = _make_plan(lib, cfg, target0, disps, dev, n_seg, seg_size)
+        prob = pl.prob
+        n_id = pl.n_id
+        img_shape = (seg_size if n_seg else B, 3, H, W)
+        kshape = (seg_size if n_seg else B, 4, 4)
+
         prob.seed = cfg.get("seed", 0)
-        prob.target = target.data_ptr()
-        prob.K, prob.inv_K = K.data_ptr(), inv_K.data_ptr()
-        automask = not (cfg["flags"] & PML_FLAG_NO_AUTOMASK)
-        n_id = 0 if not automask else (1 if cfg["flags"] & PML_FLAG_AVG_REPROJ else S)
+        if n_seg:
+            sg = pl.segs
+            for j in range(n_seg):
+                if target[j].shape != img_shape or K[j].shape != kshape or inv_K[j].shape != kshape:
+                    raise ValueError("chunk %d of the batch has the wrong shape" % j)
+                sg.target[j], sg.K[j], sg.inv_K[j] = target[j].data_ptr(), K[j].data_ptr(), inv_K[j].data_ptr()
+                for f in range(S):
+                    if sources[f][j].shape != img_shape:
+                        raise ValueError("source %d, chunk %d has the wrong shape" % (f, j))
+                    sg.sources[f][j] = sources[f][j].data_ptr()
+            prob.target, prob.K, prob.inv_K = target[0].data_ptr(), K[0].data_ptr(), inv_K[0].data_ptr()
+            for f in range(S):
+                prob.sources[f] = sources[f][0].data_ptr()
+        else:
+            if K.shape != kshape or inv_K.shape != kshape:
+                raise ValueError("K / inv_K must be [B,4,4]")
+            prob.target, prob.K, prob.inv_K = target.data_ptr(), K.data_ptr(), inv_K.data_ptr()
+            for f in range(S):
+                if sources[f].shape != img_shape:
+                    raise ValueError("source %d has the wrong shape" % f)
+                prob.sources[f] = sources[f].data_ptr()
         for f in range(S):
-            if sources[f].shape != target.shape or Ts[f].shape != (B, 4, 4):
-                raise ValueError("source / pose %d has the wrong shape" % f)
-            prob.sources[f] = sources[f].data_ptr()
+            if Ts[f].shape != (B, 4, 4):
+                raise ValueError("pose %d must be [B,4,4]" % f)
             prob.T[f] = Ts[f].data_ptr()
-        if K.shape != (B, 4, 4) or inv_K.shape != (B, 4, 4):
-            raise ValueError("K / inv_K must be [B,4,4]")
 
+        f32 = dict(device=dev, dtype=torch.float32)
         emit_depth, emit_warped = cfg.get("emit_depth", ()), cfg.get("emit_warped", ())
-        argmins, depths, warpeds, gdisps, gfws = [], [], [], [], []
+        argmin_all = torch.empty((n_pass, B, H, W), device=dev, dtype=torch.uint8)
+        small = torch.empty(pl.small_total if want_grad else pl.small_off["gconst"], **f32)
+        garena = torch.empty(pl.gdisp_total, **f32) if want_grad else None
+        so = pl.small_off
+        depths, warpeds, gdisps, gfws = [], [], [], []
+        am_ptr, n_img = argmin_all.data_ptr(), B * H * W
         for i in range(n_pass):
             d = disps[i]
             if d.dim() != 4 or d.shape[0] != B or d.shape[1] != 1:
                 raise ValueError("disp %d must be [B,1,h,w]" % i)
-            hd, wd = d.shape[2], d.shape[3]
-            if colors[i].shape != (B, 3, hd, wd):
-                raise ValueError("smoothness colour %d must match its disparity: %s vs %s"
-                                 % (i, tuple(colors[i].shape), tuple(d.shape)))
+            hd, wd = pl.shapes[i]
             ps = prob.passes[i]
-            ps.hd, ps.wd = hd, wd
-            ps.smooth_weight = cfg["smooth_weights"][i]
-            ps.disp, ps.smooth_color = d.data_ptr(), colors[i].data_ptr()
+            cshape = (seg_size if n_seg else B, 3, hd, wd)
+            if n_seg:
+                for j in range(n_seg):
+                    if colors[i][j].shape != cshape:
+                        raise ValueError("smoothness colour %d, chunk %d must match its disparity" % (i, j))
+                    pl.segs.smooth_color[i][j] = colors[i][j].data_ptr()
+                ps.smooth_color = colors[i][0].data_ptr()
+            else:
+                if colors[i].shape != cshape:
+                    raise ValueError("smoothness colour %d must match its disparity: %s vs %s"
+                                     % (i, tuple(colors[i].shape), tuple(d.shape)))
+                ps.smooth_color = colors[i].data_ptr()
+            ps.disp = d.data_ptr()
             if noise[i] is not None:
                 if tuple(noise[i].shape) != (B, n_id, H, W):
                     raise ValueError("noise %d must be [B,%d,H,W]" % (i, n_id))
                 ps.noise = noise[i].data_ptr()
-            am = torch.empty((B, H, W), device=dev, dtype=torch.uint8)
-            ps.argmin = am.data_ptr()
-            argmins.append(am)
+            else:
+                ps.noise = None
+            ps.argmin = am_ptr + i * n_img
             dp = torch.empty((B, 1, H, W), **f32) if i in emit_depth else None
             wp = torch.empty((S, B, 3, H, W), **f32) if i in emit_warped else None
             ps.depth, ps.warped = _ptr(dp), _ptr(wp)
             depths.append(dp)
             warpeds.append(wp)
             if want_grad:
-                g = torch.empty_like(d)
+                g = garena[pl.gdisp_off[i]:pl.gdisp_off[i] + B * hd * wd].view(B, 1, hd, wd)
                 ps.grad_disp = g.data_ptr()
                 gdisps.append(g)
+            else:
+                ps.grad_disp = None
             if fws[i] is not None:
                 if tuple(fws[i].shape) != (B, S, H, W):
                     raise ValueError("frame weights %d must be [B,%d,H,W] (the predictive mask at full resolution)" % (i, S))
@@ -127,91 +227,115 @@ class _PhotometricLoss(torch.autograd.Function):
                     gw = torch.empty_like(fws[i])
                     ps.grad_frame_weight = gw.data_ptr()
                     gfws.append(gw)
-        losses4 = torch.empty((n_pass, 4), **f32)
-        loss = torch.empty((n_pass,), **f32)
-        prob.losses, prob.loss_vector = losses4.data_ptr(), loss.data_ptr()
+                else:
+                    ps.grad_frame_weight = None
+            else:
+                ps.frame_weight = ps.grad_frame_weight = None
+        sp = small.data_ptr()
+        prob.losses, prob.loss_vector, prob.loss_total = sp + 4 * so["terms"], sp + 4 * so["vec"], sp + 4 * so["total"]
         if want_grad:
-            grad_T = torch.empty((n_pass, S, B, 4, 4), **f32)
-            grad_const = torch.empty((n_pass, B), **f32)
-            prob.grad_T, prob.grad_disp_const = grad_T.data_ptr(), grad_const.data_ptr()
+            prob.grad_disp_const, prob.grad_T = sp + 4 * so["gconst"], sp + 4 * so["gT"]
+        else:
+            prob.grad_disp_const = prob.grad_T = None
 
         prof = cfg.get("prof_events")
         if prof is not None:
             prob.prof_start, prob.prof_stop = prof[0].cuda_event, prof[1].cuda_event
-        ws_bytes = lib.pml_workspace_bytes(ctypes.byref(prob))
-        if ws_bytes == 0:
-            raise _cabi.PmlError("pml_workspace_bytes rejected the problem (unsupported shape: H/hd must be a "
-                                 "power of two shared by both axes, S <= %d, scales <= %d)" % (PML_MAX_SOURCES, PML_MAX_PASSES))
-        ws = torch.empty((ws_bytes + 15) // 16 * 16, device=dev, dtype=torch.uint8)
+        else:
+            prob.prof_start = prob.prof_stop = None
+        if pl.ws_bytes < 0:
+            pl.ws_bytes = lib.pml_workspace_bytes(ctypes.byref(prob))
+            if pl.ws_bytes == 0:
+                del _PLANS[key]
+                raise _cabi.PmlError("pml_workspace_bytes rejected the problem (unsupported shape: H/hd must be a "
+                                     "power of two shared by both axes, S <= %d, scales <= %d)" % (PML_MAX_SOURCES, PML_MAX_PASSES))
+            pl.ws = torch.empty((pl.ws_bytes + 15) // 16 * 16, device=dev, dtype=torch.uint8)
         fn = lib.pml_loss_forward_backward if want_grad else lib.pml_loss_forward
-        lib.check(fn(ctypes.byref(prob), _ptr(ws), ws_bytes, _stream_ptr(target)),
+        lib.check(fn(ctypes.byref(prob), _ptr(pl.ws), pl.ws_bytes, ctypes.c_void_p(stream)),
                   "pml_loss_forward_backward" if want_grad else "pml_loss_forward")
 
         ctx.want_grad = want_grad
-        ctx.cfg = cfg
         ctx.set_materialize_grads(False)   # no zero-filled grads for the non-differentiable by-products
         if want_grad:
-            ctx.gdisps, ctx.grad_T, ctx.grad_const, ctx.gfws = gdisps, grad_T, grad_const, gfws
-            ctx.shapes = [(d.shape[2], d.shape[3]) for d in disps]
-            ctx.B, ctx.S, ctx.consumed = B, S, False
-        outs = [loss, losses4] + argmins + [t for t in depths if t is not None] + [t for t in warpeds if t is not None]
-        ctx.mark_non_differentiable(*outs[1:])
-        ctx.layout = (n_pass, [t is not None for t in depths], [t is not None for t in warpeds])
+            ctx.plan, ctx.gdisps, ctx.small, ctx.gfws, ctx.garena = pl, gdisps, small, gfws, garena
+            ctx.dims = (n_pass, S, B, has_fw, stream)
+            ctx.consumed = False
+        loss_vec = small[so["vec"]:so["vec"] + n_pass]
+        total = small[so["total"]:so["total"] + 1].view(())
+        terms = small[:4 * n_pass].view(n_pass, 4)
+        outs = [loss_vec, total, terms, argmin_all] + [t for t in depths if t is not None] + [t for t in warpeds if t is not None]
+        ctx.mark_non_differentiable(*outs[2:])
         return tuple(outs)
 
     @staticmethod
-    def backward(ctx, g_loss, *unused):
-        n_pass, S = ctx.cfg["n_pass"], ctx.cfg["S"]
+    def backward(ctx, g_vec, g_total, *unused):
         n_in = len(ctx.needs_input_grad)
-        if not ctx.want_grad or g_loss is None:
+        if not ctx.want_grad or (g_vec is None and g_total is None):
             return (None,) * n_in
         if ctx.consumed:
             raise RuntimeError("libpml photometric-loss gradients were already consumed in place by a previous "
                                "backward(); re-run the forward pass instead of retain_graph")
         ctx.consumed = True
         lib = get_library()
-        up = g_loss.contiguous().to(torch.float32)
-        B = ctx.B
-        gT_out = torch.empty((S, B, 4, 4), device=up.device, dtype=torch.float32)
-        hd = (ctypes.c_int32 * n_pass)(*[s[0] for s in ctx.shapes])
-        wd = (ctypes.c_int32 * n_pass)(*[s[1] for s in ctx.shapes])
-        gptrs = (ctypes.c_void_p * n_pass)(*[g.data_ptr() for g in ctx.gdisps])
-        lib.check(lib.pml_scale_grads(n_pass, B, S, hd, wd, gptrs, _ptr(ctx.grad_const), _ptr(ctx.grad_T),
-                                      _ptr(up), _ptr(gT_out), _stream_ptr(up)), "pml_scale_grads")
+        pl = ctx.plan
+        n_pass, S, B, has_fw, stream = ctx.dims
+        if g_vec is not None:
+            g_vec = g_vec.contiguous().to(torch.float32)
+        if g_total is not None:
+            g_total = g_total.contiguous().to(torch.float32)
+        small = ctx.small
+        so = pl.small_off
+        gT_out = torch.empty((S, B, 4, 4), device=small.device, dtype=torch.float32)
+        gdisps, gfws = ctx.gdisps, ctx.gfws
+        for i in range(n_pass):
+            pl.gptrs[i] = gdisps[i].data_ptr()
+        sp = small.data_ptr()
+        lib.check(lib.pml_scale_grads(n_pass, B, S, pl.hd, pl.wd, pl.gptrs, sp + 4 * so["gconst"], sp + 4 * so["gT"],
+                                      _ptr(g_vec), _ptr(g_total), pl.prob.loss_total_div, _ptr(gT_out),
+                                      ctypes.c_void_p(stream)), "pml_scale_grads")
         need = ctx.needs_input_grad[1:]
         # hand the gradient buffers over without keeping a reference: AccumulateGrad then adopts them as
         # the leaves' .grad instead of cloning them (one 5.9 MB copy kernel per scale-0 disparity otherwise)
-        gdisps, gfws = ctx.gdisps, ctx.gfws
-        ctx.gdisps = ctx.gfws = ctx.grad_T = ctx.grad_const = None
+        ctx.gdisps = ctx.gfws = ctx.small = ctx.garena = None
         grads: List[Optional[torch.Tensor]] = [None]
         for i in range(n_pass):
             grads.append(gdisps[i] if need[i] else None)
         for f in range(S):
             grads.append(gT_out[f] if need[n_pass + f] else None)
-        for i, gw in enumerate(gfws):   # d loss_s / d mask_s, scaled by the incoming gradient
-            grads.append(gw.mul_(up[i]) if need[n_pass + S + i] else None)
+        if gfws:   # d loss_s / d mask_s, scaled by the incoming gradient
+            up = (g_vec if g_vec is not None else 0) + (g_total / pl.prob.loss_total_div if g_total is not None else 0)
+            for i, gw in enumerate(gfws):
+                grads.append(gw.mul_(up[i] if up.dim() else up) if need[n_pass + S + i] else None)
         del gdisps, gfws
-        grads += [None] * (len(need) + 1 - len(grads))
+        grads += [None] * (n_in - len(grads))
         return tuple(grads)
 
 
-def photometric_loss(target, sources: Sequence[torch.Tensor], K, inv_K, Ts: Sequence[torch.Tensor],
-                     disps: Sequence[torch.Tensor], smooth_colors: Sequence[torch.Tensor], *,
+def photometric_loss(target, sources: Sequence, K, inv_K, Ts: Sequence[torch.Tensor],
+                     disps: Sequence[torch.Tensor], smooth_colors: Sequence, *,
                      smooth_weights: Sequence[float], min_depth=0.1, max_depth=100.0,
                      no_ssim=False, disable_automasking=False, avg_reprojection=False,
                      noise: Optional[Sequence[torch.Tensor]] = None, seed: int = 0,
                      emit_depth: Sequence[int] = (), emit_warped: Sequence[int] = (), prof_events=None,
-                     frame_weights: Optional[Sequence[torch.Tensor]] = None):
+                     frame_weights: Optional[Sequence[torch.Tensor]] = None, kernel: str = "sweep",
+                     total_div: Optional[float] = None):
     """Fused view synthesis + photometric loss for ``len(disps)`` scales sharing one image set.
 
     Returns a dict: ``loss`` [n_pass] (differentiable w.r.t. ``disps`` and ``Ts``; element s is
-    the reference's ``losses["loss/s"]``, trainer.py:618), ``terms`` [n_pass,4] (loss, photometric
-    mean, smoothness, 0), ``argmin`` list of uint8 [B,H,W] (torch.min index, trainer.py:604),
-    ``depth`` {pass: [B,1,H,W]} and ``warped`` {pass: [S,B,3,H,W]} for the requested passes.
+    the reference's ``losses["loss/s"]``, trainer.py:618), ``total`` 0-dim = sum(loss) / total_div
+    (``losses["loss"]``, trainer.py:621, when total_div is the number of scales -- the default),
+    ``terms`` [n_pass,4] (loss, photometric mean, smoothness, 0), ``argmin`` list of uint8 [B,H,W]
+    (torch.min index, trainer.py:604), ``depth`` {pass: [B,1,H,W]} and ``warped`` {pass: [S,B,3,H,W]}
+    for the requested passes.
+
+    ``target``, every ``sources[f]``, ``K``, ``inv_K`` and every ``smooth_colors[i]`` are either one tensor
+    over the whole batch or -- the sequence trainer's layout (trainer_gru.py:890-899,943-957) -- a list of
+    equally sized chunks along the batch dimension, which the kernels then read in place (no torch.cat).
 
     ``frame_weights`` (one [B,S,H,W] tensor per scale, differentiable) is the ``--predictive_mask``
     ablation (trainer.py:571-579): the mask, already resized to H x W, multiplies each frame's
-    reprojection loss before the mean / min; like the reference it needs ``disable_automasking``."""
+    reprojection loss before the mean / min; like the reference it needs ``disable_automasking``.
+    ``kernel="cta"`` runs the first-generation CTA-strip kernel (testing: an independent cross-check)."""
     n_pass, S = len(disps), len(sources)
     if not (1 <= n_pass <= PML_MAX_PASSES):
         raise ValueError("1..%d scales per call" % PML_MAX_PASSES)
@@ -220,23 +344,48 @@ def photometric_loss(target, sources: Sequence[torch.Tensor], K, inv_K, Ts: Sequ
     if len(Ts) != S or len(smooth_colors) != n_pass or len(smooth_weights) != n_pass:
         raise ValueError("inconsistent argument lengths")
     flags = (PML_FLAG_NO_SSIM if no_ssim else 0) | (PML_FLAG_NO_AUTOMASK if disable_automasking else 0) | \
-            (PML_FLAG_AVG_REPROJ if avg_reprojection else 0)
+            (PML_FLAG_AVG_REPROJ if avg_reprojection else 0) | (PML_FLAG_KERNEL_CTA if kernel == "cta" else 0)
     use_noise = noise is not None and not disable_automasking
     if frame_weights is not None:
         if not disable_automasking:
             raise ValueError("frame_weights (predictive mask) are only used with disable_automasking (trainer.py:556,571)")
         if len(frame_weights) != n_pass:
             raise ValueError("one frame-weight tensor per scale")
+    # chunked batch?
+    tl = _tensor_list(target)
+    n_seg = 0
+    if tl is not None:
+        n_seg = len(tl)
+        if not (1 <= n_seg <= _cabi.PML_MAX_SEGMENTS):
+            raise ValueError("1..%d chunks per batch" % _cabi.PML_MAX_SEGMENTS)
+        if kernel == "cta":
+            raise ValueError("the CTA-strip cross-check kernel takes whole-batch tensors only")
+        groups = [tl, _tensor_list(K), _tensor_list(inv_K)] + [_tensor_list(x) for x in sources] + \
+                 [_tensor_list(x) for x in smooth_colors]
+        if any(g is None or len(g) != n_seg for g in groups):
+            raise ValueError("target, sources, K, inv_K and smooth_colors must all be lists of %d chunks" % n_seg)
+    elif any(_tensor_list(x) is not None for x in [K, inv_K] + list(sources) + list(smooth_colors)):
+        raise ValueError("target, sources, K, inv_K and smooth_colors must all be tensors or all be lists of chunks")
+    nondiff = [target, K, inv_K] + list(sources) + list(smooth_colors) + (list(noise) if use_noise else [])
+    for x in nondiff:
+        for t in (x if isinstance(x, (list, tuple)) else (x,)):
+            if isinstance(t, torch.Tensor) and t.requires_grad:
+                raise NotImplementedError(
+                    "gradients with respect to images / intrinsics / noise are not produced by libpml "
+                    "(the reference never requests them: colour inputs carry no grad, trainer.py:233-237)")
+    images = dict(target=target, K=K, inv_K=inv_K, sources=list(sources), colors=list(smooth_colors),
+                  noise=list(noise) if use_noise else None, n_seg=n_seg)
     cfg = dict(n_pass=n_pass, S=S, flags=flags, min_depth=float(min_depth), max_depth=float(max_depth),
                smooth_weights=[float(w) for w in smooth_weights], has_noise=use_noise, seed=int(seed) & (2 ** 64 - 1),
                emit_depth=tuple(emit_depth), emit_warped=tuple(emit_warped), prof_events=prof_events,
-               has_fw=frame_weights is not None)
-    tensors = list(disps) + list(Ts) + (list(frame_weights) if frame_weights is not None else []) + [target, K, inv_K] + list(sources) + list(smooth_colors)
-    if use_noise:
-        tensors += list(noise)
+               has_fw=frame_weights is not None, images=images,
+               total_div=float(total_div) if total_div else None)
+    tensors = list(disps) + list(Ts) + (list(frame_weights) if frame_weights is not None else [])
     outs = _PhotometricLoss.apply(cfg, *tensors)
-    res = {"loss": outs[0], "terms": outs[1], "argmin": list(outs[2:2 + n_pass]), "depth": {}, "warped": {}}
-    k = 2 + n_pass
+    am = outs[3]
+    res = {"loss": outs[0], "total": outs[1], "terms": outs[2], "argmin": [am[i] for i in range(n_pass)],
+           "argmin_all": am, "depth": {}, "warped": {}}
+    k = 4
     for i in sorted(set(emit_depth)):
         res["depth"][i] = outs[k]
         k += 1
@@ -244,6 +393,24 @@ def photometric_loss(target, sources: Sequence[torch.Tensor], K, inv_K, Ts: Sequ
         res["warped"][i] = outs[k]
         k += 1
     return res
+
+
+def selection_masks(argmin_all: torch.Tensor, n_id: int) -> torch.Tensor:
+    """``outputs["identity_selection/{s}"]`` (trainer.py:606-608) for all scales in one launch:
+    uint8 selection indices [n_pass,B,H,W] -> float [n_pass,B,H,W], 1 where a reprojection candidate won."""
+    lib = get_library()
+    if argmin_all.dtype != torch.uint8 or argmin_all.dim() != 4:
+        raise TypeError("argmin must be uint8 [n_pass,B,H,W]")
+    if not argmin_all.is_cuda and not lib.emulator:
+        raise RuntimeError("argmin is on %s: libpml has no CPU path" % argmin_all.device)
+    argmin_all = argmin_all.contiguous()
+    n_pass = argmin_all.shape[0]
+    n_pix = argmin_all[0].numel()
+    out = torch.empty(argmin_all.shape, device=argmin_all.device, dtype=torch.float32)
+    a = (ctypes.c_void_p * n_pass)(*[argmin_all.data_ptr() + i * n_pix for i in range(n_pass)])
+    o = (ctypes.c_void_p * n_pass)(*[out.data_ptr() + 4 * i * n_pix for i in range(n_pass)])
+    lib.check(lib.pml_selection_masks(n_pass, n_pix, a, int(n_id), o, _stream_ptr(argmin_all)), "pml_selection_masks")
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -271,6 +438,17 @@ class _DispToDepth(torch.autograd.Function):
         lib.check(lib.pml_disp_to_depth_bwd(_ptr(disp), _ptr(gs), _ptr(gd), _ptr(g), disp.numel(),
                                             ctx.rng[0], ctx.rng[1], _stream_ptr(disp)), "pml_disp_to_depth_bwd")
         return g, None, None
+
+
+def depth_from_disp(disp: torch.Tensor, min_depth: float, max_depth: float) -> torch.Tensor:
+    """``disp_to_depth(disp)[1]`` (layers.py:16-25) without an autograd node: the ``outputs[("depth", 0, s)]``
+    by-product of trainer.py:480, which nothing back-propagates through."""
+    lib = get_library()
+    disp = _check(disp.detach(), "disp", lib)
+    depth = torch.empty_like(disp)
+    lib.check(lib.pml_disp_to_depth_fwd(_ptr(disp), None, _ptr(depth), disp.numel(), float(min_depth), float(max_depth),
+                                        _stream_ptr(disp)), "pml_disp_to_depth_fwd")
+    return depth
 
 
 class _Backproject(torch.autograd.Function):

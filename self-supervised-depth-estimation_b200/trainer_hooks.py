@@ -24,6 +24,10 @@ Extra, optional knobs (all default to the reference's behaviour or cheaper equiv
                          "host": torch.randn on the CPU generator, exactly trainer.py:594-595
     opt.pml_emit_depth   "scale0" (default; compute_depth_losses reads only that) | "all" | "none"
     opt.pml_emit_warped  False (default) | True
+    opt.pml_emit_selection  True (default): outputs["identity_selection/{s}"] written by compute_losses (one
+                         launch for all scales) | "lazy" (set by install(): the patched Trainer.log fills it and the
+                         warped scale-0 images right before the tensorboard logger reads them) | False
+    opt.pml_kernel       "sweep" (default) | "cta" (first-generation kernel, cross-check only)
 """
 from __future__ import annotations
 
@@ -41,15 +45,29 @@ def _opt(opt, name, default):
 
 
 def _gather(inputs, key, n_seq, cache):
-    """trainer_gru.py:890-899,943-957 concatenates per-timestep tensors on the fly; do it once."""
+    """trainer_gru.py:890-899,943-957 concatenates the per-timestep tensors for every scale and frame; here they
+    are handed to the kernels as a list of chunks and read in place (pml_segments) -- no torch.cat."""
     if key in cache:
         return cache[key]
     if n_seq and (key + (0,)) in inputs:
-        val = torch.cat([inputs[key + (i,)] for i in range(n_seq)], 0)
+        val = [inputs[key + (i,)] for i in range(n_seq)]
     else:
         val = inputs[key]
     cache[key] = val
     return val
+
+
+class _Pending:
+    """Result of the fused call, parked in ``outputs`` between generate_images_pred and compute_losses.  The
+    reference moves every entry of ``outputs`` with ``.to(device)`` in between (trainer.py:369-371)."""
+    def __init__(self, res):
+        self.res = res
+
+    def to(self, *args, **kwargs):
+        return self
+
+
+_PENDING_KEY = "pml/pending"
 
 
 def _run_fused(self, inputs, outputs):
@@ -61,7 +79,8 @@ def _run_fused(self, inputs, outputs):
     n_seq = _opt(opt, "len_sequence", 0) if variant == "gru" else 0
     H, W = opt.height, opt.width
     scales = list(opt.scales)
-    posecnn = (variant == "trainer" and _opt(opt, "pose_model_type", "") == "posecnn")
+    # trainer.py:490-499 and trainer_fusion.py:446-456 scale the translation by the mean inverse depth
+    posecnn = (variant in ("trainer", "fusion") and _opt(opt, "pose_model_type", "") == "posecnn")
     per_scale_images = (opt.v1_multiscale and variant != "fusion")
     emit_depth = _opt(opt, "pml_emit_depth", "scale0")
     emit_warped = bool(_opt(opt, "pml_emit_warped", False))
@@ -87,7 +106,7 @@ def _run_fused(self, inputs, outputs):
     if automask and noise_mode != "host":
         seed = int(torch.empty((), dtype=torch.int64).random_().item())
 
-    res = {"loss": {}, "terms": {}, "argmin": {}, "n_id": n_id}
+    res = {"loss": {}, "terms": {}, "argmin": {}, "n_id": n_id, "total": None, "argmin_all": None, "sources": sources}
     for group in groups:
         src_scale = group[0] if per_scale_images else 0
         target = _gather(inputs, ("color", 0, src_scale), n_seq, cache)
@@ -119,7 +138,7 @@ def _run_fused(self, inputs, outputs):
             if posecnn and f != "s":
                 # trainer.py:490-499: translation scaled by the mean inverse depth of this scale
                 d = outputs[("disp", group[0])]
-                if not per_scale_images:
+                if not per_scale_images and tuple(d.shape[2:]) != (H, W):
                     d = F.interpolate(d, [H, W], mode="bilinear", align_corners=False)
                 lo, hi = 1.0 / opt.max_depth, 1.0 / opt.min_depth
                 mean_inv_depth = (lo + (hi - lo) * d).mean(3, True).mean(2, True)
@@ -135,16 +154,20 @@ def _run_fused(self, inputs, outputs):
             # (368 vs 418 us at the headline size); nothing back-propagates through this entry
             for i in ed:
                 d = disps[i].detach()
-                if d.shape[2:] != target.shape[2:]:
-                    d = _F.upsample_bilinear(d, target.shape[2], target.shape[3])     # trainer.py:474-475
-                outputs[("depth", 0, group[i])] = _F._DispToDepth.apply(d, opt.min_depth, opt.max_depth)[1]
+                t0 = target[0] if isinstance(target, list) else target
+                if d.shape[2:] != t0.shape[2:]:
+                    d = _F.upsample_bilinear(d, t0.shape[2], t0.shape[3])     # trainer.py:474-475
+                outputs[("depth", 0, group[i])] = _F.depth_from_disp(d, opt.min_depth, opt.max_depth)
             ed = []
         out = _F.photometric_loss(
             target, srcs, K, inv_K, Ts, disps, colors, smooth_weights=weights,
             min_depth=opt.min_depth, max_depth=opt.max_depth, no_ssim=opt.no_ssim,
             disable_automasking=opt.disable_automasking, avg_reprojection=opt.avg_reprojection,
             noise=[noise[s] for s in group] if noise else None, seed=seed + 7919 * scales.index(group[0]),
-            emit_depth=ed, emit_warped=ew, frame_weights=fws if pmask else None)
+            emit_depth=ed, emit_warped=ew, frame_weights=fws if pmask else None,
+            kernel=_opt(opt, "pml_kernel", "sweep"), total_div=len(scales))
+        if len(groups) == 1 and not pmask:
+            res["total"], res["argmin_all"] = out["total"], out["argmin_all"]
         for i, s in enumerate(group):
             res["loss"][s] = out["loss"][i] + bces[i] if pmask else out["loss"][i]
             res["terms"][s] = out["terms"][i]
@@ -154,8 +177,8 @@ def _run_fused(self, inputs, outputs):
             if i in out["warped"]:
                 for fi, f in enumerate(sources):
                     outputs[("color", f, s)] = out["warped"][i][fi]
-                    if automask:
-                        outputs[("color_identity", f, s)] = srcs[fi]   # trainer.py:513-515
+                    if automask:   # trainer.py:513-515
+                        outputs[("color_identity", f, s)] = torch.cat(srcs[fi], 0) if isinstance(srcs[fi], list) else srcs[fi]
     return res
 
 
@@ -179,12 +202,11 @@ def ingest_colors(inputs, frame_ids, num_scales=4, device=None, non_blocking=Tru
 
 
 def generate_images_pred(self, inputs, outputs):
-    """trainer.py:465-515.  Runs the fused sweep (warp + loss + adjoint) and parks the loss terms on
-    ``self`` for :func:`compute_losses`; writes ``outputs[("depth", 0, s)]`` (and the warped images
-    when requested).  ``outputs`` only ever receives tensors, so the reference's blanket
+    """trainer.py:465-515.  Runs the fused sweep (warp + loss + adjoint) and parks the loss terms in
+    ``outputs`` for :func:`compute_losses`; writes ``outputs[("depth", 0, s)]`` (and the warped images
+    when requested).  Everything put into ``outputs`` answers ``.to(device)``, so the reference's blanket
     ``outputs[key] = ipt.to(device)`` loop (trainer.py:369-371) keeps working."""
-    res = _run_fused(self, inputs, outputs)
-    self._pml_pending = (id(outputs), res)
+    outputs[_PENDING_KEY] = _Pending(_run_fused(self, inputs, outputs))
 
 
 def compute_reprojection_loss(self, pred, target):
@@ -200,23 +222,69 @@ def compute_reprojection_loss(self, pred, target):
 def compute_losses(self, inputs, outputs):
     """trainer.py:531-622: returns ``{"loss/{s}": ..., "loss": ...}`` and fills
     ``outputs["identity_selection/{s}"]``."""
-    pending = getattr(self, "_pml_pending", None)
-    if pending is None or pending[0] != id(outputs):
-        res = _run_fused(self, inputs, outputs)
-    else:
-        res = pending[1]
-    self._pml_pending = None
+    pending = outputs.pop(_PENDING_KEY, None)
+    res = pending.res if isinstance(pending, _Pending) else _run_fused(self, inputs, outputs)
     losses = {}
-    total = 0
-    for s in self.opt.scales:
-        loss = res["loss"][s]
-        total = total + loss
-        losses["loss/{}".format(s)] = loss
-        if not self.opt.disable_automasking and _opt(self.opt, "pml_emit_selection", True):
-            outputs["identity_selection/{}".format(s)] = (res["argmin"][s] > res["n_id"] - 1).float()
+    scales = list(self.opt.scales)
+    for s in scales:
+        losses["loss/{}".format(s)] = res["loss"][s]
         outputs[("argmin", s)] = res["argmin"][s]
-    losses["loss"] = total / self.num_scales
+    if res["total"] is not None and self.num_scales == len(scales):
+        losses["loss"] = res["total"]            # (loss_0 + loss_1 + ...) / num_scales, written by the library
+    else:
+        total = 0
+        for s in scales:
+            total = total + res["loss"][s]
+        losses["loss"] = total / self.num_scales
+    mode = _opt(self.opt, "pml_emit_selection", True)
+    if not self.opt.disable_automasking:
+        if mode == "lazy":
+            outputs["pml/selection"] = _Pending((res["argmin"], res["n_id"]))
+        elif mode:
+            _fill_selection(outputs, res["argmin"], res["n_id"], scales, res["argmin_all"])
     return losses
+
+
+def _fill_selection(outputs, argmin, n_id, scales, argmin_all=None):
+    """outputs["identity_selection/{s}"] = (idxs > n_id - 1).float() (trainer.py:606-608), one launch for all scales."""
+    if argmin_all is None:   # scales evaluated by separate calls (v1_multiscale: different resolutions)
+        for s in scales:
+            outputs["identity_selection/{}".format(s)] = _F.selection_masks(argmin[s].unsqueeze(0), n_id)[0]
+        return
+    masks = _F.selection_masks(argmin_all, n_id)
+    for i, s in enumerate(scales):
+        outputs["identity_selection/{}".format(s)] = masks[i]
+
+
+def materialize_logged_outputs(self, inputs, outputs):
+    """What ``Trainer.log`` reads beyond the losses (trainer.py:676-698) and the fused path does not produce by
+    default: ``outputs[("color", f, 0)]`` -- the warped scale-0 images, trainer.py:679-682 -- and
+    ``outputs["identity_selection/{s}"]``.  Computed on demand (a forward-only sweep of scale 0 with the
+    by-product stores enabled), i.e. only on the steps that log."""
+    opt = self.opt
+    sel = outputs.pop("pml/selection", None)
+    if isinstance(sel, _Pending):
+        argmin, n_id = sel.res
+        _fill_selection(outputs, argmin, n_id, list(opt.scales))
+    sources = list(_opt(opt, "pml_sources", [-1, 1]))
+    if all(("color", f, 0) in outputs for f in sources) or 0 not in opt.scales:
+        return
+    with torch.no_grad():
+        o2 = type(opt)(**vars(opt)) if hasattr(opt, "__dict__") else opt
+        o2.scales, o2.pml_emit_warped, o2.pml_emit_depth, o2.pml_noise = [0], True, "none", "philox"
+        shim = _Shim(o2, self.device, self.num_scales)
+        tmp = {k: v for k, v in outputs.items() if isinstance(k, tuple) and k[0] in ("disp", "cam_T_cam", "axisangle", "translation")}
+        if "predictive_mask" in outputs:
+            tmp["predictive_mask"] = outputs["predictive_mask"]
+        _run_fused(shim, inputs, tmp)
+        for f in sources:
+            if ("color", f, 0) in tmp:
+                outputs[("color", f, 0)] = tmp[("color", f, 0)]
+
+
+class _Shim:
+    def __init__(self, opt, device, num_scales):
+        self.opt, self.device, self.num_scales = opt, device, num_scales
 
 
 DEPTH_METRIC_NAMES = ["de/abs_rel", "de/sq_rel", "de/rms", "de/log_rms", "da/a1", "da/a2", "da/a3"]   # trainer.py:121-122
@@ -245,19 +313,33 @@ def install(trainer_module, variant=None):
     name = getattr(trainer_module, "__name__", "trainer").split(".")[-1]
     variant = variant or _VARIANTS.get(name, "trainer")
 
-    def _gen(self, inputs, outputs):
+    def _defaults(self):
         if not hasattr(self.opt, "pml_variant"):
             self.opt.pml_variant = variant
+        if not hasattr(self.opt, "pml_emit_selection") and orig_log is not None:
+            self.opt.pml_emit_selection = "lazy"     # the patched log() below fills it when it is read
+
+    def _gen(self, inputs, outputs):
+        _defaults(self)
         return generate_images_pred(self, inputs, outputs)
 
     def _loss(self, inputs, outputs):
-        if not hasattr(self.opt, "pml_variant"):
-            self.opt.pml_variant = variant
+        _defaults(self)
         return compute_losses(self, inputs, outputs)
+
+    orig_log = getattr(cls, "log", None)
+
+    def _log(self, mode, inputs, outputs, losses):
+        _defaults(self)
+        materialize_logged_outputs(self, inputs, outputs)
+        return orig_log(self, mode, inputs, outputs, losses)
 
     cls.generate_images_pred = _gen
     cls.compute_reprojection_loss = compute_reprojection_loss
     cls.compute_losses = _loss
+    if orig_log is not None and not getattr(orig_log, "_pml_wrapped", False):
+        _log._pml_wrapped = True
+        cls.log = _log
     if hasattr(cls, "compute_depth_losses"):
         cls.compute_depth_losses = compute_depth_losses
     for sym in ("BackprojectDepth", "Project3D", "SSIM", "disp_to_depth", "get_smooth_loss",

@@ -74,7 +74,7 @@ def run_product(opt, inputs, outputs, variant="trainer", device="cuda", noise_se
             if f != "s":
                 out[("cam_T_cam", 0, f)].requires_grad_(True)
                 leaves["grad_T/%s" % f] = out[("cam_T_cam", 0, f)]
-                if variant == "trainer" and getattr(opt, "pose_model_type", "") == "posecnn":   # trainer.py:490-499
+                if variant in ("trainer", "fusion") and getattr(opt, "pose_model_type", "") == "posecnn":   # trainer.py:490-499
                     for k in ("axisangle", "translation"):
                         out[(k, 0, f)].requires_grad_(True)
                         leaves["grad_%s/%s" % (k, f)] = out[(k, 0, f)]

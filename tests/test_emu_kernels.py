@@ -47,15 +47,47 @@ def test_three_sources_with_stereo(emu_lib):
 @pytest.mark.parametrize("sources,over", [((-1, 1, -2, 2), {}), ((-1, 1, "s"), dict(avg_reprojection=True)),
                                           ((-1, 1, -2, 2, -3, 3, -4, 4), {}), ((-1, 1, -2, 2, "s"), {}),
                                           ((-1, 1, -2), dict(disable_automasking=True)), ((-1, 1, -2, 2), dict(no_ssim=True))])
-def test_more_than_two_sources_pair_sweeps(emu_lib, sources, over, monkeypatch):
+def test_more_than_two_sources_pair_sweeps(emu_lib, sources, over):
     # S > 2: forward sweeps of all pairs but the last -> last pair's sweep selects -> adjoint sweeps of the others
-    # (three frames default to the CTA-strip kernel; force the pair sweeps here)
-    monkeypatch.setenv("PML_KERNEL", "sweep")
     B, H, W = 1, 32, 64
     opt = synthetic.make_options(H, W, batch_size=B, **over)
     inputs, outputs = synthetic.make_batch(B, H, W, sources=sources, seed=6)
     got = common.run_product(opt, inputs, outputs, "trainer", device="cpu", noise_seed=4, sources=sources)
     parity.check(got, opt, "trainer", inputs, outputs, 4, sources=sources)
+
+
+PHILOX_CASES = [((-1, 1), 64, 160), ((-1, 1, "s"), 32, 64), ((-1, 1, -2, 2), 32, 64),
+                ((-1, 1, -2, 2, -3, 3, -4, 4), 32, 64)]
+
+
+@pytest.mark.parametrize("sources,H,W", PHILOX_CASES)
+def test_default_training_instantiation(emu_lib, sources, H, W):
+    """The configuration bench.py times and trainer_hooks runs by default: tie-break noise drawn in-kernel
+    (Philox), no by-product stores -> sweep_kernel<GRAD,SSIM,MODE,EMIT=false,COMMON=true> (mode 0 for two
+    frames, modes 1/3/2 for more).  Loss, selection (where the float64 margin exceeds the noise bound) and
+    gradients against the zero-noise float64 oracle (trainer.py:592-604)."""
+    B = 2
+    opt = synthetic.make_options(H, W, batch_size=B)
+    inputs, outputs = synthetic.make_batch(B, H, W, sources=sources, seed=11)
+    torch.manual_seed(5)
+    got = common.run_product(opt, inputs, outputs, "trainer", device="cpu", noise_seed=None, sources=sources,
+                             extra_opt=dict(pml_emit_warped=False, pml_emit_depth="scale0"))
+    assert not any(k.startswith("color/") for k in got)
+    parity.check(got, opt, "trainer", inputs, outputs, 0, sources=sources, philox=True,
+                 loss_tol=parity.LOSS_TOL if B * H * W >= 20000 else parity.LOSS_TOL_SMALL)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_seed_sweep_small(emu_lib, seed):
+    """Fresh seeds at the goldens' own size (32x64) and at 64x160, alternating image styles: parity must not
+    depend on the choice of seed.  (The GPU suite runs the full seeds x sizes x styles grid.)"""
+    style = "kitti" if seed % 2 == 0 else "uniform"
+    for (H, W) in ((32, 64),) + (((64, 160),) if seed < 4 else ()):
+        opt = synthetic.make_options(H, W, batch_size=2)
+        inputs, outputs = synthetic.make_batch(2, H, W, seed=100 + seed, style=style)
+        got = common.run_product(opt, inputs, outputs, "trainer", device="cpu", noise_seed=seed + 4)
+        parity.check(got, opt, "trainer", inputs, outputs, seed + 4,
+                     loss_tol=parity.LOSS_TOL if 2 * H * W >= 20000 else parity.LOSS_TOL_SMALL)
 
 
 def test_philox_noise_path_runs_and_is_deterministic(emu_lib):

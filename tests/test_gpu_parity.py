@@ -66,16 +66,69 @@ def test_against_oracle(cuda_lib, name):
     print(name, rep)
 
 
+PHILOX_CASES = {
+    # (sources, B, H, W): mode 0 at the headline resolution, modes 1/3/2 with three, four and eight frames
+    "s2_192x640": ((-1, 1), 2, 192, 640),
+    "s2_odd_72x200": ((-1, 1), 3, 72, 200),
+    "s3_stereo_96x320": ((-1, 1, "s"), 2, 96, 320),
+    "s4_64x160": ((-1, 1, -2, 2), 2, 64, 160),
+    "s8_64x160": ((-1, 1, -2, 2, -3, 3, -4, 4), 2, 64, 160),
+}
+
+
+@pytest.mark.parametrize("name", list(PHILOX_CASES))
+def test_default_training_instantiation(cuda_lib, name):
+    """The instantiations bench.py times and trainer_hooks runs by default -- in-kernel Philox noise, no
+    by-product stores: sweep_kernel<GRAD,SSIM,MODE,EMIT=false,COMMON=true> -- against the zero-noise float64
+    oracle: loss, selection wherever the float64 margin exceeds the noise bound, gradients (forced selection)."""
+    sources, B, H, W = PHILOX_CASES[name]
+    opt = synthetic.make_options(H, W, batch_size=B)
+    inputs, outputs = synthetic.make_batch(B, H, W, sources=sources, seed=11)
+    torch.manual_seed(5)
+    got = common.run_product(opt, inputs, outputs, "trainer", device="cuda", noise_seed=None, sources=sources,
+                             extra_opt=dict(pml_emit_warped=False, pml_emit_depth="scale0"))
+    assert not any(k.startswith("color/") for k in got)
+    rep = parity.check(got, opt, "trainer", inputs, outputs, 0, sources=sources, philox=True)
+    print(name, rep)
+
+
+@pytest.mark.parametrize("size", [(32, 64), (64, 160), (96, 320)])
+@pytest.mark.parametrize("seed", range(12))
+def test_seed_sweep(cuda_lib, seed, size):
+    """12 fresh seeds x 3 sizes, image styles alternating: parity must not depend on the seed."""
+    H, W = size
+    style = "kitti" if seed % 2 == 0 else "uniform"
+    opt = synthetic.make_options(H, W, batch_size=2)
+    inputs, outputs = synthetic.make_batch(2, H, W, seed=100 + seed, style=style)
+    got = common.run_product(opt, inputs, outputs, "trainer", device="cuda", noise_seed=seed + 4)
+    parity.check(got, opt, "trainer", inputs, outputs, seed + 4,
+                 loss_tol=parity.LOSS_TOL if 2 * H * W >= 20000 else parity.LOSS_TOL_SMALL)
+
+
+def test_tensors_on_a_non_current_device(cuda_lib):
+    """The reference trainer keeps its tensors on cuda:1 / cuda:3 without ever calling set_device
+    (trainer.py:44,67): every libpml launch must follow its tensors' device, not the current one."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    assert torch.cuda.current_device() == 0
+    B, H, W = 2, 64, 160
+    opt = synthetic.make_options(H, W, batch_size=B)
+    inputs, outputs = synthetic.make_batch(B, H, W, seed=3)
+    got = common.run_product(opt, inputs, outputs, "trainer", device="cuda:1", noise_seed=7)
+    assert torch.cuda.current_device() == 0
+    parity.check(got, opt, "trainer", inputs, outputs, 7)
+
+
 @pytest.mark.parametrize("kernel", ["cta", "sweep"])
-def test_kernel_generations_agree(cuda_lib, kernel, monkeypatch):
+def test_kernel_generations_agree(cuda_lib, kernel):
     """The CTA-strip kernel and the warp-strip sweep (pair sweeps for S > 2) are interchangeable:
     each passes the same parity check."""
-    monkeypatch.setenv("PML_KERNEL", kernel)
     for sources in ((-1, 1), (-1, 1, "s")):
         B, H, W = 2, 96, 320
         opt = synthetic.make_options(H, W, batch_size=B)
         inputs, outputs = synthetic.make_batch(B, H, W, sources=sources, seed=41)
-        got = common.run_product(opt, inputs, outputs, "trainer", device="cuda", noise_seed=6, sources=sources)
+        got = common.run_product(opt, inputs, outputs, "trainer", device="cuda", noise_seed=6, sources=sources,
+                                 extra_opt=dict(pml_kernel=kernel))
         parity.check(got, opt, "trainer", inputs, outputs, 6, sources=sources)
 
 
