@@ -10,12 +10,17 @@ scales 0-3, automask + SSIM, fp32.  metric = target pixels (B*H*W) processed per
 
 ours:       value    = CUDA-graph replay of the step with inputs resident in HBM, rotating over
                        input sets whose total exceeds L2 so every step starts cold; CUDA events.
-            e2e      = the reference-facing drop-in call (Trainer.generate_images_pred +
-                       compute_losses + backward), inputs in pinned HOST memory, H2D copies and the
-                       D2H read of the loss inside the timed region.
-            e2e_u8_ingest = the same loop fed with the uint8 scale-0 frames the image decoder delivers;
-                       trainer_hooks.ingest_colors builds the fp32 colour pyramid on the device (bit-exact
-                       with the reference's PIL + ToTensor preprocessing), 3.2x fewer bytes on the link.
+            e2e      = the reference-facing drop-in call (trainer_hooks.ingest_colors + Trainer.generate_images_pred
+                       + compute_losses + backward), inputs in pinned HOST memory, H2D copies and the D2H read of
+                       the loss inside the timed region.  The host holds what the image decoder delivers -- uint8
+                       scale-0 frames -- and ingest_colors builds the fp32 colour pyramid on the device, bit-exact
+                       with the reference's PIL + ToTensor preprocessing (mono_dataset.py:99-111).
+            e2e_fp32_pyramid = the same loop with the host holding the reference DataLoader's fp32 pyramids
+                       (3.2x the bytes on the link; PCIe-bound, secondary).
+            c3 / c4  = BASELINE configs[2] (S=3 incl. stereo, 320x1024, B=8) and configs[3] (sequence trainer
+                       layout, 5 time steps as separate tensors, B=5) timed the same way as `value`.
+            ddp_step = configs[2] as a whole training step: stock ResNet-18 networks under DDP (NCCL gradient
+                       all-reduce), fused loss through the drop-ins; images/s over all ranks.
             roofline = algorithmic bytes of the fused sweep kernel / its CUDA-event duration.
             cpu_baseline = the CPU oracle (port of the reference's ATen recipe) on the host cores.
 reference:  the reference's own CPU implementation of the path.  /root/reference is pure Python
@@ -44,6 +49,18 @@ WORKLOAD = dict(workload="configs[1]: mono (frame_ids 0 -1 1) photometric loss f
                 scales=[0, 1, 2, 3])
 
 
+def config_dict(args):
+    """`config` of the JSON line -- identical for both arms (the driver compares them)."""
+    srcs = [-1, 1, -2, 2, -3, 3, -4, 4][:args.sources]
+    n_pix = args.batch * args.height * args.width
+    q_sum = sum(4.0 ** -s for s in WORKLOAD["scales"])
+    set_mb = (3 * (1 + len(srcs)) + q_sum + 3 * (q_sum - 1)) * n_pix * 4 / 1e6   # images + disps + smoothing pyramid
+    return dict(WORKLOAD, batch_per_gpu=args.batch, height=args.height, width=args.width, sources=srcs,
+                l2="GPU arm: rotating %d input sets (%.0f MB in total > 126 MB L2), every step starts L2-cold"
+                   % (args.sets, args.sets * set_mb),
+                timing="GPU arm: CUDA events around K CUDA-graph replays, max over ranks; CPU arm: perf_counter per step")
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -56,6 +73,7 @@ def parse():
     ap.add_argument("--sources", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the c3 / c4 / ddp_step arms")
     ap.add_argument("--sets", type=int, default=4, help="rotating input sets (total must exceed L2)")
     return ap.parse_args()
 
@@ -228,9 +246,10 @@ def run_ours(args, rank, world, dev):
         pass
     peak = peaks.get("hbm_gbs", 6650.0)
     achieved = kern_bytes / (kern_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, inst = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("photometric_kernel_bytes_per_launch")
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic, inst = tj.get("sweep_kernel_bytes_per_launch"), tj.get("sweep_kernel_inst_executed_per_launch")
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": ("sweep_kernel<GRAD,SSIM> (S=%d)" if S <= 2 else "photometric_kernel<S=%d,GRAD,SSIM>") % S, "achieved": round(achieved, 1),
@@ -241,15 +260,25 @@ def run_ours(args, rank, world, dev):
                 "step_frac_of_peak": round(synthetic.algorithmic_bytes(args.batch, args.height, args.width, S, n)
                                            / (ms_total / K * 1e-3) / 1e9 / peak, 4)}
 
+    # the bound that actually binds this kernel: issue slots.  executed warp-instructions per launch (ncu, profiles/)
+    # / CUDA-event duration against 148 SMs x 4 schedulers x 1 instruction per clock at the clock sampled under load
+    roofline_issue = None
+    if inst and clk.get("sm_mhz") and S == 2 and (args.batch, args.height, args.width) == (12, 192, 640):
+        peak_i = 148 * 4 * clk["sm_mhz"] * 1e6
+        roofline_issue = {"bound": "issue", "inst_executed_per_launch": int(inst), "achieved": round(inst / (kern_ms * 1e-3) / 1e9, 1),
+                          "peak": round(peak_i / 1e9, 1), "unit": "Gwarp-inst/s", "frac": round(inst / (kern_ms * 1e-3) / peak_i, 4),
+                          "source": "smsp__inst_executed.sum of the ncu capture in profiles/ (same kernel, same workload)"}
+
     # ---- end-to-end arms: Trainer drop-ins, pinned host inputs, H2D + D2H inside the region --
     # "fp32": the strict drop-in -- the host holds what the reference's DataLoader yields (fp32 colour
     #         pyramids of all frames, mono_dataset.py:99-111) and uploads them like trainer.py:233-237.
     # "u8":   SURVEY 8 row f1 -- the host holds the uint8 scale-0 frames (what the image decoder
     #         delivers); trainer_hooks.ingest_colors builds the fp32 pyramid on the device (bit-exact with
     #         PIL + ToTensor), so a quarter of the colour bytes cross the PCIe link.
-    e2e, e2e_u8 = None, None
+    e2e, e2e_fp32 = None, None
 
     def e2e_arm(mode):
+        from ssde_b200 import hostio
         o2 = SimpleNamespace(**vars(opt))
         o2.pml_sources, o2.pml_variant, o2.pml_noise = srcs, "trainer", "philox"
         o2.pml_emit_depth, o2.pml_emit_selection = "scale0", True
@@ -257,37 +286,36 @@ def run_ours(args, rank, world, dev):
         frames = [0] + list(srcs)
         host = []
         for (i, o) in sets:
+            hb = {}
             if mode == "u8":
-                hi = {("color_u8", f): (i[("color", f, 0)].permute(0, 2, 3, 1) * 255.0).round().clamp(0, 255)
-                      .to(torch.uint8).contiguous().pin_memory() for f in frames}
-                hi.update({k: v.pin_memory() for k, v in i.items() if not (isinstance(k, tuple) and k[0] == "color")})
+                hb["color_u8"] = torch.stack([(i[("color", f, 0)].permute(0, 2, 3, 1) * 255.0).round().clamp(0, 255)
+                                             .to(torch.uint8) for f in frames], 0).contiguous()     # [F,B,H,W,3]
+                hb.update({k: v for k, v in i.items() if not (isinstance(k, tuple) and k[0] == "color")})
             else:
-                hi = {k: v.pin_memory() for k, v in i.items()
-                      if not (isinstance(k, tuple) and k[0] == "color" and k[1] != 0 and k[2] != 0)}
-            ho = {k: v.pin_memory() for k, v in o.items() if k[0] in ("disp", "cam_T_cam")}
-            host.append((hi, ho))
-        h2d = sum(v.numel() * v.element_size() for v in list(host[0][0].values()) + list(host[0][1].values()))
+                hb.update({k: v for k, v in i.items()
+                           if not (isinstance(k, tuple) and k[0] == "color" and k[1] != 0 and k[2] != 0)})
+            hb.update({k: v for k, v in o.items() if k[0] in ("disp", "cam_T_cam")})
+            host.append(hostio.PinnedBatch(hb))      # one pinned arena per batch: a single H2D copy per step
+        h2d = host[0].nbytes
 
-        # Double-buffered like a DataLoader with pin_memory: the H2D copies of step i+1 run on a copy
+        # Double-buffered like a DataLoader with pin_memory: the H2D copy of step i+1 runs on a copy
         # stream while the kernels of step i run on the compute stream.  Every step still uploads its
         # own inputs from pinned host memory and reads its loss back inside the timed region.
         copy_stream = torch.cuda.Stream(device=dev)
         main_stream = torch.cuda.current_stream(dev)
 
-        def upload(hi, ho):
+        def upload(hb):
             with torch.cuda.stream(copy_stream):
-                inp = {k: v.to(dev, non_blocking=True) for k, v in hi.items()}
-                out = {k: v.to(dev, non_blocking=True) for k, v in ho.items()}
+                d, arena = hb.upload(dev)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
-            return inp, out, ev
+            return d, arena, ev
 
-        def compute(inp, out, ev):
+        def compute(d, arena, ev):
             main_stream.wait_event(ev)
-            for v in list(inp.values()) + list(out.values()):
-                v.record_stream(main_stream)
-            for k, v in out.items():
-                v.requires_grad_(True)
+            arena.record_stream(main_stream)
+            inp = {k: v for k, v in d.items() if not (isinstance(k, tuple) and k[0] in ("disp", "cam_T_cam"))}
+            out = {k: v.requires_grad_(True) for k, v in d.items() if isinstance(k, tuple) and k[0] in ("disp", "cam_T_cam")}
             if mode == "u8":
                 trainer_hooks.ingest_colors(inp, frames, len(opt.scales), device=dev)
             trainer_hooks.generate_images_pred(ns, inp, out)
@@ -296,18 +324,18 @@ def run_ours(args, rank, world, dev):
             return losses["loss"]
 
         def run_steps(n):
-            nxt = upload(*host[0])
+            nxt = upload(host[0])
             last = None
             for i in range(n):
                 cur = nxt
                 if i + 1 < n:
-                    nxt = upload(*host[(i + 1) % len(host)])
+                    nxt = upload(host[(i + 1) % len(host)])
                 loss = compute(*cur)
                 last = loss.item()   # D2H read of the step's result
             return last
 
-        Ke = max(3, min(K, 50))
-        run_steps(3)
+        Ke = max(3, min(K, 100))
+        run_steps(5)
         barrier()
         t0 = time.perf_counter()
         run_steps(Ke)
@@ -316,27 +344,194 @@ def run_ours(args, rank, world, dev):
         t = torch.tensor([dt], device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        api = "trainer_hooks.generate_images_pred + compute_losses + loss.backward(); pinned-host inputs, " \
-              "H2D of step i+1 overlapped with the kernels of step i (copy stream), loss.item() every step"
+        api = "trainer_hooks.generate_images_pred + compute_losses + loss.backward(); inputs packed in one pinned host " \
+              "arena per batch (hostio.PinnedBatch), one H2D copy per step overlapped with the kernels of the previous " \
+              "step (copy stream), loss.item() every step"
         if mode == "u8":
             api = "trainer_hooks.ingest_colors (uint8 scale-0 frames -> fp32 pyramid on the device) + " + api
         return {"value": round(world * n_pix * Ke / t.item() / 1e6, 2), "unit": UNIT,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4, "steps": Ke,
-                "ms_per_step": round(t.item() / Ke * 1e3, 4), "api": api}
+                "ms_per_step": round(t.item() / Ke * 1e3, 4), "copies_declared": True, "host_input": mode, "api": api}
 
     if not args.no_e2e:
-        e2e = e2e_arm("fp32")
-        e2e_u8 = e2e_arm("u8")
+        e2e = e2e_arm("u8")
+        e2e_fp32 = e2e_arm("fp32")
+
+    extra = {}
+    if not args.no_extra:
+        extra["c3"] = config_arm(dev, world, barrier, batch=8, height=320, width=1024, sources=[-1, 1, "s"], steps=min(K, 60),
+                                 label="configs[2] loss only: mono+stereo (0 -1 1 s), 320x1024, batch 8 per GPU")
+        extra["c4"] = gru_arm(dev, world, barrier, n_seq=5, steps=min(K, 100))
+        extra["ddp_step"] = ddp_step_arm(dev, rank, world, barrier, steps=min(K, 20))
 
     res = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
            "ms_per_step": round(ms_total / K, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
-           "config": dict(WORKLOAD, batch_per_gpu=args.batch, height=args.height, width=args.width, sources=srcs,
-                          l2="rotating %d input sets (%.0f MB in total > 126 MB L2): every step starts L2-cold"
-                             % (len(sets), len(sets) * set_mb),
-                          timing="CUDA events around K CUDA-graph replays, max over ranks"),
-           "clocks": clk, "e2e": e2e, "e2e_u8_ingest": e2e_u8, "gpu_launches": kernels_per_step * K, "roofline": roofline}
+           "config": config_dict(args),
+           "clocks": clk, "e2e": e2e, "e2e_fp32_pyramid": e2e_fp32, "gpu_launches": kernels_per_step * K, "roofline": roofline}
+    res["roofline_issue"] = roofline_issue
+    res.update(extra)
     return res
+
+
+# ------------------------------------------------------------------------------------------------
+# other BASELINE.json configurations, reported as extra keys of the same JSON line
+# ------------------------------------------------------------------------------------------------
+def _time_graphs(graphs, steps, dev, world, barrier):
+    import torch.distributed as dist
+    for i in range(3):
+        graphs[i % len(graphs)].replay()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        graphs[i % len(graphs)].replay()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.item() / steps
+
+
+def _capture(step_fns):
+    graphs, keep = [], []
+    side = torch.cuda.Stream()
+    for st in step_fns:
+        for _ in range(2):
+            st()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            st()
+            side.synchronize()
+            with torch.cuda.graph(g, stream=side):
+                keep.append(st())
+        graphs.append(g)
+    torch.cuda.synchronize()
+    return graphs, keep
+
+
+def config_arm(dev, world, barrier, batch, height, width, sources, steps, label):
+    """Device-resident fwd+bwd of the fused loss for another BASELINE configuration (CUDA-graph replay over
+    rotating input sets, like `value`)."""
+    from ssde_b200 import synthetic
+    opt = synthetic.make_options(height, width, batch_size=batch)
+    n_sets = 2
+    fns = []
+    for i in range(n_sets):
+        inputs, outputs = synthetic.make_batch(batch, height, width, sources=sources, seed=500 + i)
+        if "s" in sources:
+            outputs[("cam_T_cam", 0, "s")] = inputs["stereo_T"]
+        fns.append(fused_step_fn(opt, sources, inputs, outputs, dev))
+    graphs, keep = _capture(fns)
+    ms = _time_graphs(graphs, steps, dev, world, barrier)
+    n_pix = batch * height * width
+    S, n = len(sources), len(opt.scales)
+    bytes_step = synthetic.algorithmic_bytes(batch, height, width, S, n)
+    peak = _peak()
+    return {"workload": label, "ms_per_step": round(ms, 4), "value": round(world * n_pix / ms / 1e3, 1), "unit": UNIT,
+            "step_algorithmic_bytes": bytes_step, "step_frac_of_peak": round(bytes_step / (ms * 1e-3) / 1e9 / peak, 4)}
+
+
+def gru_arm(dev, world, barrier, n_seq, steps, height=192, width=640):
+    """configs[3]: the sequence trainer's layout (trainer_gru.py:864-1023) -- every time step a separate tensor
+    under 4-tuple keys, batch_size 1 x len_sequence 5 -- through the drop-in hooks; the kernels read the per-step
+    tensors in place (pml_segments), no torch.cat.  Device-resident, CUDA-graph replay."""
+    from types import SimpleNamespace
+    from ssde_b200 import synthetic, trainer_hooks
+    B = n_seq
+    opt = synthetic.make_options(height, width, batch_size=1, len_sequence=n_seq)
+    opt.pml_variant, opt.pml_sources, opt.pml_noise, opt.pml_emit_depth, opt.pml_emit_selection = "gru", [-1, 1], "philox", "none", False
+    ns = SimpleNamespace(opt=opt, device=dev, num_scales=len(opt.scales))
+    fns = []
+    for i in range(4):
+        inputs, outputs = synthetic.make_batch(B, height, width, seed=700 + i)
+        inp = {k: v.to(dev) for k, v in synthetic.to_sequence_layout(inputs, n_seq).items()}
+        out0 = {k: v.to(dev).requires_grad_(True) for k, v in outputs.items() if k[0] in ("disp", "cam_T_cam")}
+
+        def step(inp=inp, out0=out0):
+            out = dict(out0)
+            trainer_hooks.generate_images_pred(ns, inp, out)
+            loss = trainer_hooks.compute_losses(ns, inp, out)["loss"]
+            return torch.autograd.grad(loss, list(out0.values()))
+        fns.append(step)
+    graphs, keep = _capture(fns)
+    ms = _time_graphs(graphs, steps, dev, world, barrier)
+    n_pix = B * height * width
+    bytes_step = synthetic.algorithmic_bytes(B, height, width, 2, len(opt.scales))
+    return {"workload": "configs[3]: trainer_gru layout, %d time steps as separate tensors (4-tuple keys), 192x640, loss over "
+                        "every timestep" % n_seq, "ms_per_step": round(ms, 4), "value": round(world * n_pix / ms / 1e3, 1),
+            "unit": UNIT, "step_frac_of_peak": round(bytes_step / (ms * 1e-3) / 1e9 / _peak(), 4)}
+
+
+def ddp_step_arm(dev, rank, world, barrier, steps, batch=8, height=320, width=1024):
+    """configs[2] as a whole training step (trainer.py:233-237): stock torchvision ResNet-18 depth + pose networks
+    (tools/ddp_step_bench.py), Adam, DistributedDataParallel over NCCL for N > 1, the loss through the drop-ins."""
+    import torch.distributed as dist
+    from types import SimpleNamespace
+    try:
+        from tools import ddp_step_bench as dsb
+    except Exception as e:   # torchvision missing
+        return {"unavailable": "stock networks need torchvision: %r" % (e,)}
+    from ssde_b200 import synthetic, trainer_hooks, layers as L
+    sources = [-1, 1, "s"]
+    opt = synthetic.make_options(height, width, batch_size=batch)
+    opt.pml_sources, opt.pml_variant, opt.pml_noise, opt.pml_emit_depth, opt.pml_emit_selection = sources, "trainer", "philox", "scale0", False
+    inputs, _ = synthetic.make_batch(batch, height, width, sources=sources, seed=100 + rank)
+    inputs = {k: v.to(dev) for k, v in inputs.items()}
+    torch.manual_seed(0)
+    nets = dsb.Nets().to(dev)
+    n_params = sum(p.numel() for p in nets.parameters())
+    model = torch.nn.parallel.DistributedDataParallel(nets, device_ids=[dev.index]) if world > 1 else nets
+    optim = torch.optim.Adam(model.parameters(), 1e-4)
+    ns = SimpleNamespace(opt=opt, device=dev, num_scales=4)
+
+    def step(with_loss=True):
+        outputs = model(inputs)
+        if with_loss:
+            for f in (-1, 1):
+                outputs[("cam_T_cam", 0, f)] = L.transformation_from_parameters(
+                    outputs[("axisangle", 0, f)][:, 0], outputs[("translation", 0, f)][:, 0], f < 0)
+            trainer_hooks.generate_images_pred(ns, inputs, outputs)
+            loss = trainer_hooks.compute_losses(ns, inputs, outputs)["loss"]
+        else:   # networks only, same autograd extent: what the loss path adds to the step
+            loss = sum(outputs[("disp", s)].mean() for s in opt.scales) + \
+                sum(outputs[(k, 0, f)].sum() for k in ("axisangle", "translation") for f in (-1, 1))
+        optim.zero_grad(set_to_none=True)
+        loss.backward()
+        optim.step()
+        return loss
+
+    def timed(with_loss):
+        for _ in range(4):
+            step(with_loss)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step(with_loss)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item() / steps
+    ms = timed(True)
+    ms_nets = timed(False)
+    del model, nets, optim
+    torch.cuda.empty_cache()
+    return {"workload": "configs[2] training step: mono+stereo 320x1024, batch %d per GPU, stock ResNet-18 depth+pose networks, "
+                        "Adam, DDP over NCCL" % batch, "ms_per_step": round(ms, 3), "images_per_s": round(world * batch / ms * 1e3, 1),
+            "ms_per_step_networks_only": round(ms_nets, 3), "loss_path_ms": round(ms - ms_nets, 3),
+            "allreduce_bytes_per_step": int(n_params * 4) if world > 1 else 0, "params_M": round(n_params / 1e6, 2), "steps": steps}
+
+
+def _peak():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0)
+    except Exception:
+        return 6650.0
 
 
 # ------------------------------------------------------------------------------------------------
@@ -389,7 +584,7 @@ def run_reference(args):
     return {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(WORKLOAD, batch_per_gpu=args.batch, height=args.height, width=args.width),
+            "config": config_dict(args),
             "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                              "sample": sample},
             "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -1,8 +1,8 @@
 """Run the UNMODIFIED reference loss path on CPU (build container only).  TEST INFRASTRUCTURE.
 
 ``/root/reference`` exists only in the build container, never on the GPU box, so this module is
-used solely by ``tests/golden/make_golden.py`` (fixture generation) and by the optional
-``tests/test_oracle_vs_reference.py`` (skipped when the reference tree is absent).
+used solely by ``tests/golden/make_golden.py`` (fixture generation) and by
+``tests/test_install_reference.py`` (skipped when the reference tree is absent).
 
 How the reference is driven: ``Trainer.__init__`` cannot run (hard-coded
 ``cuda:N`` devices, KITTI on disk: trainer.py:44,67), and ``--no_cuda`` is parsed
@@ -125,7 +125,7 @@ def run(opt, inputs, outputs, variant="trainer", noise_seed=0, dtype=torch.float
         for f in (-1, 1):
             out[("cam_T_cam", 0, f)].requires_grad_(True)
             leaves["grad_T/{}".format(f)] = out[("cam_T_cam", 0, f)]
-            if variant == "trainer" and getattr(opt, "pose_model_type", "") == "posecnn":   # trainer.py:490-499
+            if variant in ("trainer", "fusion") and getattr(opt, "pose_model_type", "") == "posecnn":   # trainer.py:490-499, trainer_fusion.py:446-456
                 for k in ("axisangle", "translation"):
                     out[(k, 0, f)].requires_grad_(True)
                     leaves["grad_{}/{}".format(k, f)] = out[(k, 0, f)]

@@ -11,6 +11,7 @@ from . import _cabi  # noqa: F401
 from . import functional  # noqa: F401
 from . import layers  # noqa: F401
 from . import trainer_hooks  # noqa: F401
+from . import hostio  # noqa: F401
 from .layers import (BackprojectDepth, Project3D, SSIM, disp_to_depth,  # noqa: F401
                      get_smooth_loss, transformation_from_parameters)
 from .trainer_hooks import (generate_images_pred, compute_reprojection_loss,  # noqa: F401

@@ -136,7 +136,7 @@ class _PhotometricLoss(torch.autograd.Function):
         stream = torch.cuda.current_stream(dev).cuda_stream if target0.is_cuda else 0
 
         key = (dev, stream, B, H, W, S, n_pass, cfg["flags"], tuple(d.shape[2:] for d in disps), cfg["min_depth"],
-               cfg["max_depth"], tuple(cfg["smooth_weights"]), cfg.get("total_div"), n_seg, seg_size)
+               cfg["max_depth"], tuple(cfg["smooth_weights"]), cfg.get("total_div"), n_seg, seg_size, has_fw)
         pl = _PLANS.get(key)
         if pl is None:
             if len(_PLANS) >= _PLANS_MAX:

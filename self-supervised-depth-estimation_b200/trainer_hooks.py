@@ -187,14 +187,21 @@ def ingest_colors(inputs, frame_ids, num_scales=4, device=None, non_blocking=Tru
     (datasets/mono_dataset.py:99-111) + the fp32 upload of trainer.py:233-237.
 
     ``inputs[("color_u8", f)]``: uint8 [B,H,W,3] scale-0 frames as the decoder / PIL delivers them
-    (host, ideally pinned, or already on the device).  Fills ``inputs[("color", f, s)]`` for every
+    (host, ideally pinned, or already on the device) -- or all frames stacked in ``inputs["color_u8"]``
+    [F,B,H,W,3] in the order of ``frame_ids``.  Fills ``inputs[("color", f, s)]`` for every
     scale with exactly the tensors the reference's DataLoader would have produced, from a quarter of
     the bytes on the PCIe link.  All frames go through ONE pyramid launch chain."""
-    frames = [inputs[("color_u8", f)] for f in frame_ids]
-    dev = device if device is not None else frames[0].device
-    stacked = torch.cat([t.to(dev, non_blocking=non_blocking) for t in frames], 0)
+    if "color_u8" in inputs:          # all frames in one tensor [F,B,H,W,3] (frame order = frame_ids): no cat
+        st = inputs["color_u8"]
+        dev = device if device is not None else st.device
+        B = st.shape[1]
+        stacked = st.to(dev, non_blocking=non_blocking).reshape((-1,) + tuple(st.shape[2:]))
+    else:
+        frames = [inputs[("color_u8", f)] for f in frame_ids]
+        dev = device if device is not None else frames[0].device
+        B = frames[0].shape[0]
+        stacked = torch.cat([t.to(dev, non_blocking=non_blocking) for t in frames], 0)
     levels = _F.color_pyramid(stacked, num_scales)
-    B = frames[0].shape[0]
     for i, f in enumerate(frame_ids):
         for s in range(num_scales):
             inputs[("color", f, s)] = levels[s][i * B:(i + 1) * B]

@@ -1,6 +1,6 @@
 """Generate tests/golden/*.npz by executing the UNMODIFIED reference (build container only).
 
-    python tests/golden/make_golden.py            # needs /root/reference
+    python tests/golden/make_golden.py [case ...]  # needs /root/reference; no argument = every case
 
 For every case this script builds a small synthetic batch (package ``synthetic`` module), runs
 ``/root/reference/trainer*.py``'s ``Trainer.generate_images_pred`` + ``Trainer.compute_losses``
@@ -46,6 +46,9 @@ CASES = {
     # torch.randn stream of the automask noise -- hence this case runs without automasking (no noise drawn)
     "trainer_posecnn":      ("trainer", dict(pose_model_type="posecnn", disable_automasking=True), dict(style="kitti", seed=27)),
     "trainer_wide":         ("trainer", {}, dict(style="kitti", seed=24, batch=1, height=64, width=160)),
+    # the same translation scaling exists in trainer_fusion.py:446-456 (full-resolution disparities, no resize)
+    "fusion_posecnn":       ("fusion", dict(pose_model_type="posecnn", disable_automasking=True),
+                             dict(style="kitti", seed=28, full_res_disp=True)),
 }
 NOISE_SEED = 1234
 
@@ -65,7 +68,7 @@ def build_case(name):
 
 def main():
     assert reference_runner.available(), "needs the reference tree"
-    for name in CASES:
+    for name in (sys.argv[1:] or CASES):
         variant, opt, inputs, outputs = build_case(name)
         ref_in = synthetic.to_sequence_layout(inputs, opt.len_sequence) if variant == "gru" else inputs
         blob = {}

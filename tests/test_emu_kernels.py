@@ -104,6 +104,15 @@ def test_philox_noise_path_runs_and_is_deterministic(emu_lib):
         assert 0.4 < frac < 0.6, frac
 
 
+def test_plan_cache_separates_configurations_of_equal_shape(emu_lib):
+    """Launch plans are cached per configuration; two configurations that only differ in the predictive mask
+    (same shapes and flags, different workspace) must not share one."""
+    for name in ("trainer_noautomask", "trainer_predmask", "trainer_noautomask"):
+        variant, opt, inputs, outputs, r32, r64, seed = common.load_golden(name)
+        got = common.run_product(opt, inputs, outputs, variant, device="cpu", noise_seed=seed)
+        assert common.rel_err(got["loss"], r64["loss"]) < 1e-4
+
+
 def test_layer_dropins_match_oracle(emu_lib):
     import layer_checks
     layer_checks.run("cpu")
