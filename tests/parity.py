@@ -16,9 +16,10 @@ testable for an fp32 implementation of a piecewise-smooth function:
 * derivative kinks.  The loss has three kinds of points where the derivative jumps; a pixel whose
   float64 value sits within fp32 round-off of one may legitimately take either branch.  They are
   identified explicitly, counted, and masked -- nothing else is:
-    - ``cell``:  a bilinear sampling coordinate within a few ulps of an integer (grid_sample's slope
-                 changes from one cell to the next, trainer.py:508);
-    - ``l1``:    |warped - target| < L1_EPS in some channel (sign(x - y), trainer.py:520);
+    - ``cell``:  a bilinear sampling coordinate within fp32 round-off of an integer or of the clip limits
+                 (grid_sample's slope changes from one cell to the next / is switched off, trainer.py:508);
+    - ``l1``:    the sign of (warped - target) in some channel flips when the sampling coordinate moves by
+                 its fp32 round-off (sign(x - y), trainer.py:520);
     - ``clamp``: an SSIM value within CLAMP_EPS of 1 before the clamp (layers.py:248).  The clamp at 0 is
                  not a kink of the function: n/d <= 1 in exact arithmetic, only fp32 round-off on windows
                  with x ~ y gets there; the fused kernels follow float64 and keep the gradient.
@@ -47,9 +48,10 @@ LOSS_TOL = 1e-5
 LOSS_TOL_SMALL = 1e-4   # images with fewer than ~20k pixels: the per-pixel fp32 SSIM noise does not average out (see above)
 GRAD_TOL = 1e-4
 FLIP_SHARE = 5e-4      # near-tie selection flips allowed (observed: 1e-4 .. 3e-4 on the goldens)
-KINK_SHARE = {"cell": 2e-3, "l1": 5e-3, "clamp": 1e-3}   # caps on the share of loss pixels per kink kind
-# (observed: cell <= 7e-4 -- expected 2.4e-4 per coordinate --, l1 <= 2.5e-3 on well-aligned synthetic views, clamp 0)
-L1_EPS = 1e-6           # fp32 error of a warped colour (coordinate error x image slope)
+KINK_SHARE = {"cell": 5e-2, "l1": 5e-2, "clamp": 1e-3}   # caps on the share of loss pixels per kink kind.  Observed on the
+# KITTI-like views: cell <= 8e-4 (expected 2.4e-4 per coordinate), l1 <= 3e-3, clamp 0; the caps leave room for the iid-random stress
+# images, whose warp fields are chaotic (fp32 coordinate errors of 1e-4 px): cell up to 2e-2 there.  Every report carries the shares.
+L1_EPS = 2e-6           # floor of the |warped - target| threshold (the per-pixel threshold is 4x the fp32 oracle's own colour error)
 CLAMP_EPS = 2e-5        # fp32 error of an SSIM value near the clamp (E[x^2] - mu^2 cancellation against C2 = 9e-4)
 PHILOX_BOUND = 1.4e-4  # Box-Muller on 32-bit uniforms: |noise| <= 6.66, two candidates, x 1e-5
 
@@ -73,9 +75,15 @@ def _ssim_raw(x, y):
     return (1 - n / d) / 2
 
 
-def kink_pixels(o64, opt, variant, inputs, sources, scale, argmin):
+def kink_pixels(o64, opt, variant, inputs, sources, scale, argmin, o32=None):
     """-> dict of [B,H,W] bool maps (cell, l1, clamp) of loss pixels on a derivative kink (float64).
-    Only the candidate that ``argmin`` selects at a pixel carries gradient there, so only its kinks count."""
+    Only the candidate that ``argmin`` selects at a pixel carries gradient there, so only its kinks count.
+
+    The yardstick is the fp32 error of a sampling coordinate: ``tol`` = 16 ulps, or 4x the deviation of the
+    fp32 oracle's own coordinate from float64 in the 3x3 neighbourhood where the geometry is ill-conditioned
+    (large parallax, near the epipole; ``o32``).  ``cell``: an integer (or the clip limits 0, n-1) lies within
+    ``tol`` of the coordinate.  ``l1``: re-sampling the source at the coordinate shifted by +-tol changes the
+    sign of (warped - target) in some channel, or |warped - target| < L1_EPS."""
     n_seq = opt.len_sequence if variant == "gru" else 0
     src_scale = scale if (opt.v1_multiscale and variant != "fusion") else 0
     inp = synthetic.to_sequence_layout(inputs, opt.len_sequence) if variant == "gru" else inputs
@@ -89,14 +97,27 @@ def kink_pixels(o64, opt, variant, inputs, sources, scale, argmin):
         # slopes matter wherever one of those windows selected this frame
         sel_near = F.max_pool2d(sel[:, None].float(), 3, 1, 1)[:, 0] > 0
         g = o64["sample/%s/%d" % (f, scale)]
+        g32 = o32["sample/%s/%d" % (f, scale)].double() if o32 is not None else g
         Hs, Ws = g.shape[1], g.shape[2]
+        tols = []
         for c, n in ((0, Ws), (1, Hs)):
-            # a sampling coordinate within ~16 fp32 ulps of an integer; exactly clipped coordinates are not
-            # ambiguous (the slope is zeroed on both sides)
-            ix = (((g[..., c] + 1) * n - 1) / 2).clamp(0, n - 1)
-            cell |= sel_near & ((ix - ix.round()).abs() < 1e-6 * (ix.abs() + 16)) & (ix > 0) & (ix < n - 1)
+            ix = ((g[..., c] + 1) * n - 1) / 2
+            dev = (((g32[..., c] + 1) * n - 1) / 2 - ix).abs()
+            dev = F.max_pool2d(dev[:, None], 3, 1, 1)[:, 0]
+            tol = torch.maximum(1e-6 * (ix.abs() + 16), 4 * dev)
+            tols.append(tol)
+            # including 0 and n-1, where the clip of grid_sample's border mode switches the slope off;
+            # coordinates well outside are not ambiguous
+            cell |= sel_near & ((ix - ix.round()).abs() < tol) & (ix > -tol) & (ix < n - 1 + tol)
         x = o64["color/%s/%d" % (f, scale)].double()
-        l1 |= sel & ((x - target).abs() < L1_EPS).any(1)
+        src = po._gather(inp, ("color", f, src_scale), n_seq).double()
+        sgn = torch.sign(x - target)
+        amb = ((x - target).abs() < L1_EPS).any(1)
+        for sx in (-1.0, 1.0):
+            for sy in (-1.0, 1.0):
+                gp = torch.stack([g[..., 0] + sx * 2 * tols[0] / Ws, g[..., 1] + sy * 2 * tols[1] / Hs], -1)
+                amb |= (torch.sign(po.warp(src, gp) - target) != sgn).any(1)
+        l1 |= sel & amb
         if not opt.no_ssim:
             raw = _ssim_raw(x, target)
             clamp |= sel & ((raw - 1).abs() < CLAMP_EPS).any(1)
@@ -178,10 +199,10 @@ def check(got, opt, variant, inputs, outputs, seed, ref32=None, ref64=None, sour
     if any(k.startswith("grad_") for k in got):
         of = oracle_pair(opt, variant, inputs, outputs, seed, sources, forced=forced, zero_noise=philox)
         of32 = oracle_pair(opt, variant, inputs, outputs, seed, sources, forced=forced, dtype=torch.float32,
-                           zero_noise=philox)
-        masks, keep_w, shares = {}, {}, {}
+                           zero_noise=philox)     # forward quantities (sampling grid, warped colours) do not depend on `forced`
+        masks, keep_w, keep_w3, shares = {}, {}, {}, {}
         for s in opt.scales:
-            kinks = kink_pixels(o64, opt, variant, inputs, sources, s, forced[s])
+            kinks = kink_pixels(o64, opt, variant, inputs, sources, s, forced[s], of32)
             any_k = kinks["cell"] | kinks["l1"] | kinks["clamp"]
             shares[s] = {k: round(v.float().mean().item(), 6) for k, v in kinks.items()}
             shares[s]["any"] = round(any_k.float().mean().item(), 6)
@@ -189,6 +210,7 @@ def check(got, opt, variant, inputs, outputs, seed, ref32=None, ref64=None, sour
                 assert shares[s][kind] <= cap or degenerate, "scale %d: %.2e of the pixels sit on a '%s' kink" % (s, shares[s][kind], kind)
             keep_w[s] = (~any_k).to(torch.float64)
             m = F.max_pool2d(any_k[:, None].float(), 3, 1, 1)         # the 3x3 SSIM window around a kink pixel
+            keep_w3[s] = 1.0 - m[:, 0].to(torch.float64)
             hd = got["grad_disp/%d" % s].shape[2]
             k = m.shape[2] // hd
             if k > 1:
@@ -196,7 +218,10 @@ def check(got, opt, variant, inputs, outputs, seed, ref32=None, ref64=None, sour
             masks["grad_disp/%d" % s] = m > 0
         rep["kink_share"] = shares
         # share of every pose-type gradient carried by the kink pixels (float64, forced selection)
+        # ... and by their 3x3 neighbourhoods: where float64 sits on the switched-off side of a clip limit the kink
+        # pixel itself carries nothing, its neighbours show what the other branch would carry
         ok = oracle_pair(opt, variant, inputs, outputs, seed, sources, forced=forced, pixel_weight=keep_w, zero_noise=philox)
+        ok3 = oracle_pair(opt, variant, inputs, outputs, seed, sources, forced=forced, pixel_weight=keep_w3, zero_noise=philox)
         for k in sorted(of):
             if not k.startswith("grad_"):
                 continue
@@ -206,9 +231,9 @@ def check(got, opt, variant, inputs, outputs, seed, ref32=None, ref64=None, sour
                 keep = (~masks[k]).double()
                 a, b, b32 = a * keep, b * keep, b32 * keep
             elif not k.startswith("grad_mask"):
-                d = (of[k].double() - ok[k].double())
-                allow = 2 * d.abs().max().item() / max(of[k].abs().max().item(), 1e-300)
-                allow2 = 2 * d.norm().item() / max(of[k].double().norm().item(), 1e-300)
+                d, d3 = (of[k].double() - ok[k].double()), (of[k].double() - ok3[k].double())
+                allow = 2 * (d.abs().max().item() + d3.abs().max().item()) / max(of[k].abs().max().item(), 1e-300)
+                allow2 = 2 * (d.norm().item() + d3.norm().item()) / max(of[k].double().norm().item(), 1e-300)
             e, e2 = common.rel_err(a, b), l2_err(a, b)
             f, f2 = common.rel_err(b32, b), l2_err(b32, b)
             rep[k] = {"max": e, "l2": e2, "fp32_ref_max": f, "fp32_ref_l2": f2, "kink_allowance": allow}
@@ -226,4 +251,75 @@ def check(got, opt, variant, inputs, outputs, seed, ref32=None, ref64=None, sour
                 floor = (ref32[k].double() - o64[k]).abs().max().item() if k in ref32 else 0.0
                 e = (got[k].double() - o64[k]).abs().max().item()
                 assert e < 2e-4 + 2 * floor, "%s: max abs err %.2e (fp32 reference itself %.2e)" % (k, e, floor)
+    return rep
+
+
+def pose_gradient_check(device, opt, inputs, outputs, sources=(-1, 1)):
+    """A sharp test of the pose (and disparity) gradients: the kink pixels are taken OUT of the loss on both
+    sides instead of being bounded by an allowance.  The library runs the ``disable_automasking`` configuration
+    with per-pixel frame weights (the predictive-mask input of trainer.py:571-579, here 0 on the 3x3
+    neighbourhoods of kink pixels and 1 elsewhere); the float64 oracle weighs the same pixels out
+    (``pixel_weight``).  What is left is smooth, so GRAD_TOL + 2 x (fp32 oracle's own deviation) must hold for
+    d loss / d T without any allowance.  Returns the report."""
+    from types import SimpleNamespace
+    from ssde_b200 import functional as Fn
+    o = SimpleNamespace(**vars(opt))
+    o.disable_automasking = True
+    dev = torch.device(device)
+    scales = list(o.scales)
+    H, W = o.height, o.width
+
+    def tensors(req):
+        tgt = inputs[("color", 0, 0)].to(dev)
+        srcs = [inputs[("color", f, 0)].to(dev) for f in sources]
+        K, iK = inputs[("K", 0)].to(dev), inputs[("inv_K", 0)].to(dev)
+        Ts = [(inputs["stereo_T"] if f == "s" else outputs[("cam_T_cam", 0, f)]).to(dev).clone().requires_grad_(req) for f in sources]
+        disps = [outputs[("disp", s)].to(dev).clone().requires_grad_(req) for s in scales]
+        cols = [inputs[("color", 0, s)].to(dev) for s in scales]
+        return tgt, srcs, K, iK, Ts, disps, cols
+    kw = dict(smooth_weights=[o.disparity_smoothness / 2 ** s for s in scales], min_depth=o.min_depth, max_depth=o.max_depth,
+              disable_automasking=True)
+    tgt, srcs, K, iK, Ts, disps, cols = tensors(False)
+    first = Fn.photometric_loss(tgt, srcs, K, iK, Ts, disps, cols, **kw)
+    forced = {s: first["argmin"][i].long().cpu() for i, s in enumerate(scales)}
+    o64 = oracle_pair(o, "trainer", inputs, outputs, 0, sources)
+    o32 = oracle_pair(o, "trainer", inputs, outputs, 0, sources, dtype=torch.float32)
+    keep = {}
+    for s in scales:
+        kinks = kink_pixels(o64, o, "trainer", inputs, sources, s, forced[s], o32)
+        any_k = kinks["cell"] | kinks["l1"] | kinks["clamp"]
+        # with weight 0 every candidate of a pixel is 0 and the selection there is moot; pixels whose selection
+        # is a near-tie are weighed out too, so that both sides agree on the selection everywhere else
+        any_k |= o64["margin/%d" % s] <= TIE_EPS
+        keep[s] = 1.0 - F.max_pool2d(any_k[:, None].float(), 3, 1, 1)[:, 0]
+    tgt, srcs, K, iK, Ts, disps, cols = tensors(True)
+    fws = [keep[s][:, None].expand(-1, len(sources), -1, -1).contiguous().to(dev) for s in scales]
+    out = Fn.photometric_loss(tgt, srcs, K, iK, Ts, disps, cols, frame_weights=fws, **kw)
+    out["total"].backward()
+    kw64 = {s: keep[s].double() for s in scales}
+    sel = {s: out["argmin"][i].long().cpu() for i, s in enumerate(scales)}
+    of = oracle_pair(o, "trainer", inputs, outputs, 0, sources, forced=sel, pixel_weight=kw64)
+    of32 = oracle_pair(o, "trainer", inputs, outputs, 0, sources, forced=sel, pixel_weight=kw64, dtype=torch.float32)
+    rep = {"kept_share": {s: round(keep[s].mean().item(), 5) for s in scales}}
+    e = common.rel_err(out["total"].detach().cpu(), of["loss"])
+    rep["loss"] = e
+    assert e <= 1e-4, "loss with kink pixels weighed out: rel err %.3e" % e
+    for fi, f in enumerate(sources):
+        if f == "s":
+            continue
+        k = "grad_T/%s" % f
+        a, b, b32 = Ts[fi].grad.double().cpu(), of[k].double(), of32[k].double()
+        e, e2, fl, fl2 = common.rel_err(a, b), l2_err(a, b), common.rel_err(b32, b), l2_err(b32, b)
+        rep[k] = {"max": e, "l2": e2, "fp32_ref_max": fl, "fp32_ref_l2": fl2}
+        # d loss / d T is a cancelling sum over all pixels: both fp32 evaluations sit well above 1e-4 of float64 on it
+        # (ATen: 5e-5 .. 5e-4), the library within 3x of the ATen run's own deviation (accumulating the per-pixel
+        # terms in double changes its result in the 4th digit only: the noise is in the terms, not in the sum)
+        assert e <= GRAD_TOL + 3 * fl, "%s (kink pixels weighed out): max-norm rel err %.3e (fp32 reference itself %.3e)" % (k, e, fl)
+        assert e2 <= GRAD_TOL + 3 * fl2, "%s (kink pixels weighed out): L2 rel err %.3e (fp32 reference itself %.3e)" % (k, e2, fl2)
+    for i, s in enumerate(scales):
+        k = "grad_disp/%d" % s
+        a, b, b32 = disps[i].grad.double().cpu(), of[k].double(), of32[k].double()
+        e, fl = common.rel_err(a, b), common.rel_err(b32, b)
+        rep[k] = {"max": e, "fp32_ref_max": fl}
+        assert e <= GRAD_TOL + 2 * fl, "%s (kink pixels weighed out): max-norm rel err %.3e (fp32 reference itself %.3e)" % (k, e, fl)
     return rep

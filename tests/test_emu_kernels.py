@@ -90,6 +90,13 @@ def test_seed_sweep_small(emu_lib, seed):
                      loss_tol=parity.LOSS_TOL if 2 * H * W >= 20000 else parity.LOSS_TOL_SMALL)
 
 
+@pytest.mark.parametrize("H,W,seed,style", [(64, 160, 3, "kitti"), (48, 96, 101, "uniform")])
+def test_pose_gradient_with_kink_pixels_weighed_out(emu_lib, H, W, seed, style):
+    opt = synthetic.make_options(H, W, batch_size=2)
+    inputs, outputs = synthetic.make_batch(2, H, W, seed=seed, style=style)
+    parity.pose_gradient_check("cpu", opt, inputs, outputs)
+
+
 def test_philox_noise_path_runs_and_is_deterministic(emu_lib):
     variant, opt, inputs, outputs, r32, r64, seed = common.load_golden("trainer_static")
     torch.manual_seed(1)

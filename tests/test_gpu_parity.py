@@ -105,6 +105,17 @@ def test_seed_sweep(cuda_lib, seed, size):
                  loss_tol=parity.LOSS_TOL if 2 * H * W >= 20000 else parity.LOSS_TOL_SMALL)
 
 
+@pytest.mark.parametrize("H,W,seed,style", [(64, 160, 3, "kitti"), (96, 320, 100, "kitti"), (96, 320, 101, "uniform"),
+                                            (192, 640, 7, "kitti")])
+def test_pose_gradient_with_kink_pixels_weighed_out(cuda_lib, H, W, seed, style):
+    """Sharp gradient test: the derivative-kink pixels are removed from the loss on both sides (per-pixel frame
+    weights in the library, pixel weights in the float64 oracle) instead of being covered by an allowance."""
+    opt = synthetic.make_options(H, W, batch_size=2)
+    inputs, outputs = synthetic.make_batch(2, H, W, seed=seed, style=style)
+    rep = parity.pose_gradient_check("cuda", opt, inputs, outputs)
+    print(rep)
+
+
 def test_tensors_on_a_non_current_device(cuda_lib):
     """The reference trainer keeps its tensors on cuda:1 / cuda:3 without ever calling set_device
     (trainer.py:44,67): every libpml launch must follow its tensors' device, not the current one."""
