@@ -34,7 +34,7 @@ extern "C" {
  * (predictive mask), pml_upsample_*, pml_bce_ones_*, pml_pyramid_u8; 3 = PML_MAX_SOURCES 4 -> 8 (array sizes in
  * pml_problem) and pml_problem.loss_vector; 4 = pml_problem.loss_total / loss_total_div (the mean over scales,
  * trainer.py:621, written by the library), pml_problem.segments (per-timestep tensors of the sequence trainer consumed
- * in place), pml_scale_grads takes the upstream of the total, pml_selection_masks, PML_FLAG_KERNEL_CTA.
+ * in place), pml_scale_grads takes the upstream of the total, pml_selection_masks, pml_disp_head_*, PML_FLAG_KERNEL_CTA.
  * The Python binding refuses a library of another version. */
 #define PML_ABI_VERSION 4
 #define PML_MAX_SOURCES 8 /* source frames per target, e.g. (-1, 1, "s") = 3; BASELINE config 5 sweeps 2/4/8 */
@@ -187,6 +187,17 @@ size_t pml_bce_workspace_bytes(void);
 int pml_bce_ones_fwd(const float* mask, int64_t n, float* out, void* workspace, size_t workspace_bytes, pml_stream_t);
 int pml_bce_ones_bwd(const float* mask, const float* g_out, float* g_mask, int64_t n, pml_stream_t);
 
+
+/* ---- DepthDecoder disparity heads: networks/depth_decoder.py:46-47,62-66 over
+ * layers.Conv3x3 (layers.py:121-136): disp = sigmoid(conv3x3(reflection_pad1(x), weight) + bias), x [B,C,h,w],
+ * weight [1,C,3,3], bias [1] -> disp [B,1,h,w], one kernel.  Backward (one kernel + a fixed-order reduction):
+ * from the saved output and g_disp to g_x [B,C,h,w] (nullable), g_weight [1,C,3,3], g_bias [1]. ---- */
+int pml_disp_head_fwd(const float* x, const float* weight, const float* bias, float* disp,
+                      int32_t B, int32_t C, int32_t h, int32_t w, pml_stream_t);
+size_t pml_disp_head_bwd_workspace_bytes(int32_t B, int32_t C, int32_t h, int32_t w);
+int pml_disp_head_bwd(const float* x, const float* weight, const float* disp, const float* g_disp, float* g_x,
+                      float* g_weight, float* g_bias, void* workspace, size_t workspace_bytes,
+                      int32_t B, int32_t C, int32_t h, int32_t w, pml_stream_t);
 
 /* ---- input colour pyramid: datasets/mono_dataset.py:84-111 resizes every
  * frame on the CPU with PIL (scale i = Resize((H >> i, W >> i), Image.ANTIALIAS) of scale i-1), applies

@@ -82,6 +82,10 @@ _SIGNATURES = {
     "pml_bce_workspace_bytes": (c_size_t, []),
     "pml_bce_ones_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "pml_bce_ones_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "pml_disp_head_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "pml_disp_head_bwd_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
+    "pml_disp_head_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                  c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "pml_pyramid_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
     "pml_pyramid_u8": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, POINTER(c_void_p), c_void_p, c_size_t, c_void_p]),
     "pml_depth_metrics_workspace_bytes": (c_size_t, []),

@@ -9,6 +9,7 @@
 #include "pml_metrics.cuh"
 #include "pml_mask.cuh"
 #include "pml_pyramid.cuh"
+#include "pml_disphead.cuh"
 
 #include <math.h>
 #include <stdlib.h>

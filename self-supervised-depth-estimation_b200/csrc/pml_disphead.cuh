@@ -1,0 +1,189 @@
+// DepthDecoder disparity heads (second half): the producer of outputs[("disp", s)],
+//
+//     disp_s = sigmoid(Conv3x3(x_s))          networks/depth_decoder.py:46-47, :62-66
+//     Conv3x3 = ReflectionPad2d(1) + Conv2d(C_in, 1, 3)   layers.py:121-136,  C_in = 16 / 32 / 64 / 128 for s = 0..3
+//
+// fused into one forward and one backward kernel: the stock path pads (a full copy of x), convolves and applies
+// the sigmoid in three launches and keeps the padded copy and the pre-activation for autograd.  Both kernels are
+// HBM-bound byte movers (x is read once forward; backward reads x and writes g_x once), organised like the other
+// sweeps of this library: one warp marches down a strip of 30 owned columns (+1 halo lane each side), horizontal
+// neighbours travel by shuffles, vertical neighbours roll in registers, reflection is an index map on the loads.
+#pragma once
+#include "pml_common.cuh"
+
+namespace pml {
+
+constexpr int kHeadTW = 30;   // owned columns per strip
+constexpr int kHeadTH = 16;   // owned rows per work item
+
+struct HeadParams {
+    const float* x;       // [B,C,h,w]
+    const float* weight;  // [1,C,3,3]
+    const float* bias;    // [1]
+    float* disp;          // [B,1,h,w]  (forward: out; backward: the saved output)
+    const float* g_disp;  // [B,1,h,w]
+    float* g_x;           // [B,C,h,w] or null
+    float* part;          // [items][10]: 9 weight-gradient partials + bias partial
+    int B, C, h, w, n_strips, n_chunks;
+};
+
+__device__ __forceinline__ float sigmoidf(float z) { return __fdiv_rn(1.0f, 1.0f + expf(-z)); }
+
+// grid = B * n_chunks * n_strips work items, 32 threads; dynamic smem = C * 12 floats (weights, 3 x float4 per channel)
+__global__ void __launch_bounds__(32)
+disp_head_fwd_kernel(const HeadParams p) {
+    PML_DYN_SMEM(float, sw);
+    const int lane = threadIdx.x;
+    const int C = p.C, h = p.h, w = p.w, plane = h * w;
+    for (int i = lane; i < C * 9; i += 32) sw[(i / 9) * 12 + (i % 9)] = p.weight[i];
+    __syncwarp();
+    int item = blockIdx.x;
+    const int strip = item % p.n_strips; item /= p.n_strips;
+    const int chunk = item % p.n_chunks;
+    const int b = item / p.n_chunks;
+    const int x0 = strip * kHeadTW, x1 = min(x0 + kHeadTW, w);
+    const int y0 = chunk * kHeadTH, y1 = min(y0 + kHeadTH, h);
+    const int cx = x0 - 1 + lane;
+    const int rx = reflect1(clampi(cx, -1, w), w);
+    const bool owned = (cx >= x0) && (cx < x1);
+    const float bias = __ldg(p.bias);
+    const float* xb = p.x + (size_t)b * C * plane + rx;
+    // a0 / a1 / a2: pre-activations of the windows centred on rows r-1, r, r+1 while row r streams through
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll 1
+    for (int r = y0 - 1; r <= y1; ++r) {
+        const int ry = reflect1(clampi(r, -1, h), h);
+        const float* xr = xb + ry * w;
+#pragma unroll 4
+        for (int c = 0; c < C; ++c) {
+            const float v = __ldg(xr + (size_t)c * plane);
+            const float l = __shfl_up_sync(0xffffffffu, v, 1), rr = __shfl_down_sync(0xffffffffu, v, 1);
+            const float4* wk = reinterpret_cast<const float4*>(sw + c * 12);
+            const float4 w0 = wk[0], w1 = wk[1], w2 = wk[2];   // W[0][0..2] W[1][0] | W[1][1..2] W[2][0..1] | W[2][2]
+            a2 = fmaf(w0.x, l, fmaf(w0.y, v, fmaf(w0.z, rr, a2)));   // row r is the top row of window r+1
+            a1 = fmaf(w0.w, l, fmaf(w1.x, v, fmaf(w1.y, rr, a1)));   // ... the middle row of window r
+            a0 = fmaf(w1.z, l, fmaf(w1.w, v, fmaf(w2.x, rr, a0)));   // ... the bottom row of window r-1
+        }
+        const int py = r - 1;
+        if (owned && py >= y0 && py < y1) p.disp[(size_t)b * plane + py * w + cx] = sigmoidf(a0 + bias);
+        a0 = a1; a1 = a2; a2 = 0.f;
+    }
+}
+
+// Backward, one work item per (image, channel, chunk, strip).  With gz = g_disp * disp * (1 - disp):
+//   g_x[c](q)     = sum over windows p and taps d with reflect(p + d) = q of W[c][d] * gz(p)
+//   g_W[c][d]     = sum_p gz(p) * x_pad[c](p + d),      g_bias = sum_p gz(p)
+// The reflection adjoint folds the padded ring back: because the row and the column index maps are independent it
+// can be applied to the gz neighbourhood once per row -- l' = l + [cx == w-2] r, r' = r + [cx == 1] l, and the same
+// between the rows above / below for q == 1 and q == h-2 -- after which every channel is nine plain FMAs.
+template <bool WITH_GX>
+__global__ void __launch_bounds__(32)
+disp_head_bwd_kernel(const HeadParams p) {
+    const int lane = threadIdx.x;
+    const int C = p.C, h = p.h, w = p.w, plane = h * w;
+    int item = blockIdx.x;
+    const int strip = item % p.n_strips; item /= p.n_strips;
+    const int chunk = item % p.n_chunks; item /= p.n_chunks;
+    const int c = item % C;
+    const int b = item / C;
+    const int x0 = strip * kHeadTW, x1 = min(x0 + kHeadTW, w);
+    const int y0 = chunk * kHeadTH, y1 = min(y0 + kHeadTH, h);
+    const int cx = x0 - 1 + lane;
+    const int rx = reflect1(clampi(cx, -1, w), w);
+    const bool in_img = (cx >= 0) && (cx < w);
+    const bool owned = (cx >= x0) && (cx < x1);
+    const float f1 = (cx == 1) ? 1.f : 0.f, f2 = (cx == w - 2) ? 1.f : 0.f;
+    float W[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) W[k] = __ldg(p.weight + c * 9 + k);
+    const float* xc = p.x + ((size_t)b * C + c) * plane + rx;
+    const float* gd = p.g_disp + (size_t)b * plane;
+    const float* dd = p.disp + (size_t)b * plane;
+    float* gx = WITH_GX ? p.g_x + ((size_t)b * C + c) * plane : nullptr;
+
+    float acc[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[k] = 0.f;
+    float accb = 0.f;
+    // rolling rows r-2 (U), r-1 (M): folded gz neighbourhood (l', v, r') and x_pad neighbourhood (l, v, r)
+    float gU[3] = {0.f, 0.f, 0.f}, gM[3] = {0.f, 0.f, 0.f}, xU[3] = {0.f, 0.f, 0.f}, xM[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int r = y0 - 1; r <= y1; ++r) {
+        const int ry = reflect1(clampi(r, -1, h), h);
+        const float xv = __ldg(xc + ry * w);
+        float gz = 0.f;
+        if (r >= 0 && r < h && in_img) {
+            const float d = __ldg(dd + r * w + cx);
+            gz = __ldg(gd + r * w + cx) * d * (1.f - d);      // sigmoid backward
+        }
+        const float xl = __shfl_up_sync(0xffffffffu, xv, 1), xr = __shfl_down_sync(0xffffffffu, xv, 1);
+        const float gl = __shfl_up_sync(0xffffffffu, gz, 1), gr = __shfl_down_sync(0xffffffffu, gz, 1);
+        const float gD[3] = {gl + f2 * gr, gz, gr + f1 * gl};
+        const float xD[3] = {xl, xv, xr};
+        const int q = r - 1;                                     // output row / window row completed by row r
+        if (q >= y0 && q < y1) {
+            if (WITH_GX) {
+                const float g1 = (q == 1) ? 1.f : 0.f, g2 = (q == h - 2) ? 1.f : 0.f;
+                float s = 0.f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float u = gU[k] + g2 * gD[k], dn = gD[k] + g1 * gU[k];
+                    // neighbour k (0: left, 1: centre, 2: right) pairs with tap column 2 - k; rows above / at / below
+                    // with tap rows 2 / 1 / 0
+                    s = fmaf(W[6 + (2 - k)], u, fmaf(W[3 + (2 - k)], gM[k], fmaf(W[0 + (2 - k)], dn, s)));
+                }
+                if (owned) gx[q * w + cx] = s;
+            }
+            const float gq = owned ? gM[1] : 0.f;                // gz(q, cx)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                acc[0 + k] = fmaf(gq, xU[k], acc[0 + k]);        // x_pad row q-1
+                acc[3 + k] = fmaf(gq, xM[k], acc[3 + k]);        // row q
+                acc[6 + k] = fmaf(gq, xD[k], acc[6 + k]);        // row q+1
+            }
+            accb += gq;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { gU[k] = gM[k]; gM[k] = gD[k]; xU[k] = xM[k]; xM[k] = xD[k]; }
+    }
+    float* out = p.part + (size_t)blockIdx.x * 10;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const float v = warp_sum(acc[k]);
+        if (lane == 0) out[k] = v;
+    }
+    const float vb = warp_sum(accb);
+    if (lane == 0) out[9] = vb;
+}
+
+// fixed-order reduction of the partials: block c sums the 9 weight gradients of channel c over (image, chunk,
+// strip); block C sums the bias gradient (taken from the items of channel 0).  256 threads.
+__global__ void __launch_bounds__(256)
+disp_head_reduce_kernel(const HeadParams p, float* __restrict__ g_weight, float* __restrict__ g_bias) {
+    __shared__ double s_acc[256];
+    const int c = blockIdx.x;
+    const int per = p.n_chunks * p.n_strips;
+    const int ch = (c == p.C) ? 0 : c;
+    const int n_out = (c == p.C) ? 1 : 9;
+    for (int k = 0; k < n_out; ++k) {
+        const int col = (c == p.C) ? 9 : k;
+        double a = 0.0;
+        for (int i = threadIdx.x; i < p.B * per; i += 256) {
+            const int b = i / per, j = i - b * per;
+            a += (double)p.part[((size_t)(b * p.C + ch) * per + j) * 10 + col];
+        }
+        s_acc[threadIdx.x] = a;
+        __syncthreads();
+        for (int m = 128; m > 0; m >>= 1) {
+            if ((int)threadIdx.x < m) s_acc[threadIdx.x] += s_acc[threadIdx.x + m];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            if (c == p.C) g_bias[0] = (float)s_acc[0];
+            else g_weight[c * 9 + k] = (float)s_acc[0];
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace pml

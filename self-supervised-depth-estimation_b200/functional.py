@@ -639,6 +639,42 @@ class _BceOnes(torch.autograd.Function):
         return gm
 
 
+class _DispHead(torch.autograd.Function):
+    """sigmoid(Conv3x3(x)) of the DepthDecoder disparity heads (networks/depth_decoder.py:46-47,62-66;
+    layers.py:121-136): reflection pad + 3x3 convolution to one channel + sigmoid, one kernel each way."""
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        lib = get_library()
+        x, weight, bias = _check(x, "x", lib), _check(weight, "weight", lib), _check(bias, "bias", lib)
+        if x.dim() != 4 or weight.shape != (1, x.shape[1], 3, 3) or bias.numel() != 1:
+            raise ValueError("x [B,C,h,w], weight [1,C,3,3], bias [1] expected")
+        B, C, h, w = x.shape
+        disp = torch.empty((B, 1, h, w), device=x.device, dtype=torch.float32)
+        lib.check(lib.pml_disp_head_fwd(_ptr(x), _ptr(weight), _ptr(bias), _ptr(disp), B, C, h, w, _stream_ptr(x)),
+                  "pml_disp_head_fwd")
+        ctx.save_for_backward(x, weight, disp)
+        return disp
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = get_library()
+        x, weight, disp = ctx.saved_tensors
+        B, C, h, w = x.shape
+        g = g.contiguous().to(torch.float32)
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gw = torch.empty_like(weight)
+        gb = torch.empty((1,), device=x.device, dtype=torch.float32)
+        nb = lib.pml_disp_head_bwd_workspace_bytes(B, C, h, w)
+        ws = torch.empty(nb, device=x.device, dtype=torch.uint8)
+        lib.check(lib.pml_disp_head_bwd(_ptr(x), _ptr(weight), _ptr(disp), _ptr(g), _ptr(gx), _ptr(gw), _ptr(gb), _ptr(ws), nb,
+                                        B, C, h, w, _stream_ptr(x)), "pml_disp_head_bwd")
+        return gx, gw, gb
+
+
+def disp_head(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    return _DispHead.apply(x, weight, bias)
+
+
 def upsample_bilinear(x: torch.Tensor, height: int, width: int) -> torch.Tensor:
     return _Upsample.apply(x, int(height), int(width))
 

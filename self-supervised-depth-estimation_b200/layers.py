@@ -79,3 +79,46 @@ def interpolate_bilinear(x, size):
     """The reference's ``F.interpolate(x, [H, W], mode="bilinear", align_corners=False)`` calls
     (trainer.py:474-475 on disparities, :574-576 on the predictive mask): [B,C,h,w] -> [B,C,H,W]."""
     return _F.upsample_bilinear(x, size[0], size[1])
+
+
+class DispHead(nn.Module):
+    """``sigmoid(Conv3x3(x))`` -- one disparity head of the reference's ``DepthDecoder``
+    (networks/depth_decoder.py:46-47 ``("dispconv", s)``, :62-66) as one fused kernel.
+
+    Wraps the reference's own ``Conv3x3`` module (layers.py:121-136) and keeps using ITS parameters:
+    ``self.conv`` is the original ``nn.Conv2d(C_in, 1, 3)``, so state_dict keys, optimiser state and
+    checkpoints are unchanged.  ``forward`` returns the disparity (the sigmoid is inside)."""
+
+    def __init__(self, conv3x3):
+        super().__init__()
+        conv = getattr(conv3x3, "conv", conv3x3)
+        if not isinstance(conv, nn.Conv2d) or conv.out_channels != 1 or tuple(conv.kernel_size) != (3, 3):
+            raise TypeError("DispHead wraps a Conv3x3 / nn.Conv2d(C_in, 1, 3)")
+        pad = getattr(conv3x3, "pad", None)
+        if pad is not None and not isinstance(pad, nn.ReflectionPad2d):
+            raise TypeError("DispHead implements the reflection-padded Conv3x3 (use_refl=True, layers.py:127-128)")
+        self.pad = pad if pad is not None else nn.ReflectionPad2d(1)
+        self.conv = conv
+
+    def forward(self, x):
+        return _F.disp_head(x, self.conv.weight, self.conv.bias)
+
+
+def install_disp_heads(depth_decoder):
+    """Replace the ``("dispconv", s)`` + ``sigmoid`` pairs of a reference ``DepthDecoder`` instance
+    (networks/depth_decoder.py:46-49,62-66) by :class:`DispHead`.  The decoder's ``forward`` is untouched: it
+    still evaluates ``self.sigmoid(self.convs[("dispconv", i)](x))`` -- the head now returns the disparity and
+    ``self.sigmoid`` becomes the identity.  Parameter names stay the same.  Returns the decoder."""
+    replaced = {}
+    for key, mod in list(depth_decoder.convs.items()):
+        if isinstance(key, tuple) and key[0] == "dispconv" and not isinstance(mod, DispHead):
+            head = DispHead(mod)
+            replaced[id(mod)] = head
+            depth_decoder.convs[key] = head
+    if hasattr(depth_decoder, "decoder"):     # the nn.ModuleList that registers the parameters
+        for i, mod in enumerate(depth_decoder.decoder):
+            if id(mod) in replaced:
+                depth_decoder.decoder[i] = replaced[id(mod)]
+    if replaced:
+        depth_decoder.sigmoid = nn.Identity()
+    return depth_decoder

