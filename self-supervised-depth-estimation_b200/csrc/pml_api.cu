@@ -31,7 +31,7 @@ struct Plan {
     int n_id;
     int smooth_blocks[PML_MAX_PASSES], smooth_off[PML_MAX_PASSES], smooth_total;
     int max_chunks;
-    size_t off_identity, off_part, off_mean, off_meanpart, off_imagepart, off_smooth, off_rp, off_argmin, total;
+    size_t off_identity, off_part, off_mean, off_meanpart, off_imagepart, off_smooth, off_rp, off_argmin, off_tstat, total;
 };
 
 inline void pml_event_record(void* ev, cudaStream_t st) {
@@ -205,6 +205,8 @@ Plan make_plan(const pml_problem* p, bool grad) {
     pl.off_meanpart = off; off = align16(off + (size_t)p->n_pass * p->B * pl.max_chunks * sizeof(float));
     pl.off_imagepart = off; off = align16(off + (size_t)p->n_pass * p->B * 4 * sizeof(float));
     pl.off_smooth = off;   off = align16(off + (size_t)pl.smooth_total * 3 * sizeof(float));
+    pl.off_tstat = off;   // target window statistics for the warp-strip sweep: [B,H,W,2] x float4
+    if (pl.sweep && !(p->flags & PML_FLAG_NO_SSIM) && pml::kSweepTstat) off = align16(off + (size_t)p->B * p->H * p->W * 8 * sizeof(float));
     pl.off_rp = pl.off_argmin = off;
     pl.two_sweeps = pl.sweep && (p->S > 2 || p->pass[0].frame_weight != nullptr);
     if (pl.two_sweeps) {   // pair-by-pair sweep: reprojection losses of all frames + a selection map
@@ -245,7 +247,8 @@ int launch_sweep(const PhotoParams& pp, cudaStream_t st) {
     if (pp.mode == 2) emit = false;   // the adjoint sweeps of earlier pairs never write by-products
     bool common = !emit && pp.pair_n == 2 && (pp.mode != 0 || pp.S == 2) &&
                   !(pp.flags & (PML_FLAG_NO_AUTOMASK | PML_FLAG_AVG_REPROJ));
-    for (int i = 0; i < pp.n_pass; ++i) common = common && pp.pass[i].noise == nullptr && pp.pass[i].fw == nullptr;
+    for (int i = 0; i < pp.n_pass; ++i)
+        common = common && pp.pass[i].noise == nullptr && pp.pass[i].fw == nullptr && (pp.mode != 0 || pp.pass[i].argmin != nullptr);
     if (pp.mode == 0) {
         if (common)    PML_LAUNCH((sweep_kernel<GRAD, SSIM, 0, false, true>), grid, blk, smem, st, pp);
         else if (emit) PML_LAUNCH((sweep_kernel<GRAD, SSIM, 0, true>), grid, blk, smem, st, pp);
@@ -323,7 +326,21 @@ int run_loss(const pml_problem* p, void* ws, size_t ws_bytes, cudaStream_t st, b
         else      PML_LAUNCH(smooth_kernel<false>, dim3(pl.smooth_total), dim3(256), 0, st, sp);
     }
 
-    // 3. identity reprojection losses (automask), once for all passes
+    // 3. identity reprojection losses (automask), once for all passes; the sweep of the first frame pair also
+    //    leaves the window statistics of the target for the fused sweep
+    float4* tstat = (pl.sweep && ssim && pml::kSweepTstat) ? reinterpret_cast<float4*>(base + pl.off_tstat) : nullptr;
+    if (pl.n_id == 0 && tstat != nullptr) {   // no automask: a statistics-only pass of the same kernel
+        IdentityParams ip{};
+        ip.target = p->target; ip.src0 = p->target; ip.src1 = p->target;
+        ip.n_seg = sp.n_seg; ip.seg_size = sp.seg_size;
+        if (sg)
+            for (int j = 0; j < sg->n_seg; ++j) ip.target_c.p[j] = ip.src0_c.p[j] = ip.src1_c.p[j] = sg->target[j];
+        ip.out = nullptr; ip.tstat = tstat; ip.B = p->B; ip.H = p->H; ip.W = p->W; ip.S = 1;
+        ip.n_out = 1; ip.TH = knobs().id_th;
+        ip.n_strips = (p->W + kPrepTW - 1) / kPrepTW;
+        ip.n_chunks = (p->H + ip.TH - 1) / ip.TH;
+        PML_LAUNCH(identity_sweep_kernel<true>, dim3(ip.n_chunks * ip.n_strips, p->B), dim3(32), 0, st, ip);
+    }
     if (pl.n_id > 0 && pl.sweep) {
         for (int fa = 0; fa < p->S; fa += 2) {   // one launch per pair of source frames
             IdentityParams ip;
@@ -335,6 +352,7 @@ int run_loss(const pml_problem* p, void* ws, size_t ws_bytes, cudaStream_t st, b
                     ip.target_c.p[j] = sg->target[j]; ip.src0_c.p[j] = sg->sources[fa][j];
                     ip.src1_c.p[j] = sg->sources[fa + pair_n - 1][j];
                 }
+            ip.tstat = (fa == 0) ? tstat : nullptr;
             ip.out = identity; ip.B = p->B; ip.H = p->H; ip.W = p->W; ip.S = pair_n;
             ip.avg = (p->flags & PML_FLAG_AVG_REPROJ) ? 1 : 0;
             ip.n_out = pl.n_id; ip.plane_off = ip.avg ? 0 : fa; ip.accumulate = (ip.avg && fa > 0) ? 1 : 0;
@@ -368,7 +386,7 @@ int run_loss(const pml_problem* p, void* ws, size_t ws_bytes, cudaStream_t st, b
     pp.min_disp = (float)(1.0 / (double)p->max_depth);                                   // layers.py:21
     pp.disp_range = (float)(1.0 / (double)p->min_depth - 1.0 / (double)p->max_depth);     // layers.py:23
     pp.eps = p->eps; pp.seed = p->seed;
-    pp.target = p->target; pp.K = p->K; pp.invK = p->inv_K; pp.identity = identity;
+    pp.target = p->target; pp.K = p->K; pp.invK = p->inv_K; pp.identity = identity; pp.tstat = tstat;
     for (int f = 0; f < PML_MAX_SOURCES; ++f) { pp.src[f] = p->sources[f]; pp.T[f] = p->T[f]; }
     int low_cells = 0;
     for (int i = 0; i < p->n_pass; ++i) {

@@ -29,14 +29,18 @@ struct HeadParams {
 
 __device__ __forceinline__ float sigmoidf(float z) { return __fdiv_rn(1.0f, 1.0f + expf(-z)); }
 
-// grid = B * n_chunks * n_strips work items, 32 threads; dynamic smem = C * 12 floats (weights, 3 x float4 per channel)
-__global__ void __launch_bounds__(32)
+// grid = B * n_chunks * n_strips work items; G = blockDim.x / 32 warps per item, warp g convolves the channels
+// g, g + G, g + 2G, ... (the low-resolution heads have 64 / 128 channels over few pixels: without the split a
+// 24 x 80 map would occupy 72 warps of the whole GPU) and the partial pre-activations of a row meet in shared
+// memory, summed in warp order by warp 0.  Dynamic smem = C * 12 floats (weights) + G * 32 floats.
+__global__ void __launch_bounds__(256)
 disp_head_fwd_kernel(const HeadParams p) {
     PML_DYN_SMEM(float, sw);
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5, G = blockDim.x >> 5;
     const int C = p.C, h = p.h, w = p.w, plane = h * w;
-    for (int i = lane; i < C * 9; i += 32) sw[(i / 9) * 12 + (i % 9)] = p.weight[i];
-    __syncwarp();
+    float* sred = sw + C * 12;
+    for (int i = threadIdx.x; i < C * 9; i += blockDim.x) sw[(i / 9) * 12 + (i % 9)] = p.weight[i];
+    __syncthreads();
     int item = blockIdx.x;
     const int strip = item % p.n_strips; item /= p.n_strips;
     const int chunk = item % p.n_chunks;
@@ -55,7 +59,7 @@ disp_head_fwd_kernel(const HeadParams p) {
         const int ry = reflect1(clampi(r, -1, h), h);
         const float* xr = xb + ry * w;
 #pragma unroll 4
-        for (int c = 0; c < C; ++c) {
+        for (int c = g; c < C; c += G) {
             const float v = __ldg(xr + (size_t)c * plane);
             const float l = __shfl_up_sync(0xffffffffu, v, 1), rr = __shfl_down_sync(0xffffffffu, v, 1);
             const float4* wk = reinterpret_cast<const float4*>(sw + c * 12);
@@ -65,7 +69,18 @@ disp_head_fwd_kernel(const HeadParams p) {
             a0 = fmaf(w1.z, l, fmaf(w1.w, v, fmaf(w2.x, rr, a0)));   // ... the bottom row of window r-1
         }
         const int py = r - 1;
-        if (owned && py >= y0 && py < y1) p.disp[(size_t)b * plane + py * w + cx] = sigmoidf(a0 + bias);
+        if (G > 1) {
+            sred[g * 32 + lane] = a0;
+            __syncthreads();
+            if (g == 0) {
+                float t = 0.f;
+                for (int k = 0; k < G; ++k) t += sred[k * 32 + lane];
+                if (owned && py >= y0 && py < y1) p.disp[(size_t)b * plane + py * w + cx] = sigmoidf(t + bias);
+            }
+            __syncthreads();
+        } else if (owned && py >= y0 && py < y1) {
+            p.disp[(size_t)b * plane + py * w + cx] = sigmoidf(a0 + bias);
+        }
         a0 = a1; a1 = a2; a2 = 0.f;
     }
 }

@@ -43,6 +43,7 @@ struct PhotoParams {
     const float* invK;
     const float* T[PML_MAX_SOURCES];
     const float* identity;  // [B, n_id, H, W] identity reprojection losses (automask)
+    const float4* tstat;    // [B, H, W, 2] target window statistics (IdentityParams::tstat), warp-strip sweep with SSIM
     PassDev pass[PML_MAX_PASSES];
     int TW, TH, n_strips, n_chunks, cta_per_pass;   // cta_per_pass: work items (CTAs or warps) per pass
     int S;            // number of source frames (run-time copy of the template parameter)
@@ -676,7 +677,8 @@ finalize_image_kernel(const FinalizeParams q) {
     if (q.with_grad && tid < q.S * 16) {
         const int f = tid >> 4, e = tid & 15, kk = e >> 2, j = e & 3;
         int bl;
-        const float* Kb = chunk_of(q.K, q.K_c, q.n_seg, q.seg_size, b, bl) + (size_t)bl * 16;
+        const float* Kc = chunk_of(q.K, q.K_c, q.n_seg, q.seg_size, b, bl);
+        const float* Kb = Kc + (size_t)bl * 16;
         const float* gp = s_col + 1 + f * 12;
         q.grad_T[((size_t)(pi * q.S + f) * q.B + b) * 16 + e] =
             fmaf(Kb[kk], gp[j], fmaf(Kb[4 + kk], gp[4 + j], Kb[8 + kk] * gp[8 + j]));

@@ -88,7 +88,8 @@ smooth_kernel(const SmoothParams q) {
         const int y = idx / w, x = idx - y * w;
         const float* d = ps.disp + (size_t)b * n;
         int bl;
-        const float* img = chunk_of(ps.color, q.color_c[pi], q.n_seg, q.seg_size, b, bl) + (size_t)bl * 3 * n;
+        const float* imgc = chunk_of(ps.color, q.color_c[pi], q.n_seg, q.seg_size, b, bl);
+        const float* img = imgc + (size_t)bl * 3 * n;
         const float inv = __fdiv_rn(1.0f, s_mean + 1e-7f);
         const float nx_ = 1.0f / ((float)q.B * (float)h * (float)(w - 1));
         const float ny_ = 1.0f / ((float)q.B * (float)(h - 1) * (float)w);

@@ -82,6 +82,7 @@ def _decoder_dropin(device):
         def forward(self, feats):
             return {("disp", s): self.sigmoid(self.convs[("dispconv", s)](feats[s])) for s in range(4)}
     torch.manual_seed(0)
+    torch.backends.cudnn.allow_tf32 = False     # the stock convolution would otherwise run in TF32 (1e-4 off)
     dec = Dec().to(device)
     feats = [torch.randn(2, 16 * 2 ** s, 32 >> s, 64 >> s, device=device) for s in range(4)]
     want = {k: v.detach() for k, v in dec(feats).items()}
