@@ -14,6 +14,9 @@
 #include <math.h>
 #include <stdlib.h>
 #include <atomic>
+#ifndef PML_HOST_EMU
+#include <nvtx3/nvToolsExt.h>   // header-only: a no-op unless a profiler (nsys / ncu) injects its library
+#endif
 
 namespace {
 
@@ -31,7 +34,7 @@ struct Plan {
     int n_id;
     int smooth_blocks[PML_MAX_PASSES], smooth_off[PML_MAX_PASSES], smooth_total;
     int max_chunks;
-    size_t off_identity, off_part, off_mean, off_meanpart, off_imagepart, off_smooth, off_rp, off_argmin, off_tstat, total;
+    size_t off_identity, off_part, off_mean, off_meanpart, off_imagepart, off_smooth, off_rp, off_argmin, total;
 };
 
 inline void pml_event_record(void* ev, cudaStream_t st) {
@@ -52,6 +55,16 @@ struct Knobs {
     }
 };
 const Knobs& knobs() { static const Knobs k; return k; }
+
+// NVTX range around a phase of an entry point (tracing); shows up in nsys / ncu timelines
+struct NvtxRange {
+#ifndef PML_HOST_EMU
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+#else
+    explicit NvtxRange(const char*) {}
+#endif
+};
 
 // RAII: make the device that owns `ptr` current for the duration of an entry point.  The reference trainers keep
 // their tensors on cuda:1 / cuda:3 and never call set_device (trainer.py:44,67); the legacy default stream handle
@@ -175,8 +188,30 @@ Plan make_plan(const pml_problem* p, bool grad) {
     bool common_fwd = p->S == 2 && !(p->flags & (PML_FLAG_NO_AUTOMASK | PML_FLAG_AVG_REPROJ));
     for (int i = 0; i < p->n_pass; ++i)
         common_fwd = common_fwd && !p->pass[i].noise && !p->pass[i].depth && !p->pass[i].warped && !p->pass[i].frame_weight;
-    pl.TH_fwd = pl.sweep ? chunk_rows(kNumSM * (common_fwd ? 24 : 18)) : chunk_rows(kNumSM * 6);
-    pl.TH = (pl.sweep && !grad) ? pl.TH_fwd : chunk_rows(pl.sweep ? kNumSM * 12 : kNumSM * 6);
+    // Warp strips: one warp per work item and `slots` resident warps per SM (8 for the forward+backward sweeps at 255
+    // registers, 12 / 16 for the forward-only ones).  All items cost the same, so the sweep takes
+    // ceil(items / (SMs * slots)) waves of (TH + 5) row steps (5 halo steps per chunk): pick the chunk count that
+    // minimises that; among equals the shorter chunks (more items: better balance, more parallelism for small
+    // problems).  Measured at the headline size (profiles/r02_ab_timings.txt): 1 chunk 0.3604 ms, 2 chunks 0.3672, 3: 0.3705.
+    auto sweep_rows = [&](int slots) {
+        if (knobs().th > 0) return knobs().th > p->H ? p->H : (knobs().th < 4 ? 4 : knobs().th);
+        const long long cap = (long long)kNumSM * slots;
+        long long best_cost = -1;
+        int best_th = p->H;
+        for (int chunks = 1; chunks <= 64; ++chunks) {
+            int th = (p->H + chunks - 1) / chunks;
+            th = ((th + 7) / 8) * 8;
+            if (th > p->H) th = p->H;
+            if (th < 16 && chunks > 1) break;
+            const int n_ch = (p->H + th - 1) / th;
+            const long long items = (long long)per_chunk * n_ch;
+            const long long cost = ((items + cap - 1) / cap) * (th + 5);
+            if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best_th = th; }
+        }
+        return best_th;
+    };
+    pl.TH_fwd = pl.sweep ? sweep_rows(common_fwd ? 16 : 12) : chunk_rows(kNumSM * 6);
+    pl.TH = (pl.sweep && !grad) ? pl.TH_fwd : (pl.sweep ? sweep_rows(8) : chunk_rows(kNumSM * 6));
     pl.n_chunks = (p->H + pl.TH - 1) / pl.TH;
     pl.n_chunks_fwd = (p->H + pl.TH_fwd - 1) / pl.TH_fwd;
     pl.cta_per_pass = p->B * pl.n_chunks * pl.n_strips;
@@ -205,8 +240,6 @@ Plan make_plan(const pml_problem* p, bool grad) {
     pl.off_meanpart = off; off = align16(off + (size_t)p->n_pass * p->B * pl.max_chunks * sizeof(float));
     pl.off_imagepart = off; off = align16(off + (size_t)p->n_pass * p->B * 4 * sizeof(float));
     pl.off_smooth = off;   off = align16(off + (size_t)pl.smooth_total * 3 * sizeof(float));
-    pl.off_tstat = off;   // target window statistics for the warp-strip sweep: [B,H,W,2] x float4
-    if (pl.sweep && !(p->flags & PML_FLAG_NO_SSIM) && pml::kSweepTstat) off = align16(off + (size_t)p->B * p->H * p->W * 8 * sizeof(float));
     pl.off_rp = pl.off_argmin = off;
     pl.two_sweeps = pl.sweep && (p->S > 2 || p->pass[0].frame_weight != nullptr);
     if (pl.two_sweeps) {   // pair-by-pair sweep: reprojection losses of all frames + a selection map
@@ -247,8 +280,7 @@ int launch_sweep(const PhotoParams& pp, cudaStream_t st) {
     if (pp.mode == 2) emit = false;   // the adjoint sweeps of earlier pairs never write by-products
     bool common = !emit && pp.pair_n == 2 && (pp.mode != 0 || pp.S == 2) &&
                   !(pp.flags & (PML_FLAG_NO_AUTOMASK | PML_FLAG_AVG_REPROJ));
-    for (int i = 0; i < pp.n_pass; ++i)
-        common = common && pp.pass[i].noise == nullptr && pp.pass[i].fw == nullptr && (pp.mode != 0 || pp.pass[i].argmin != nullptr);
+    for (int i = 0; i < pp.n_pass; ++i) common = common && pp.pass[i].noise == nullptr && pp.pass[i].fw == nullptr;
     if (pp.mode == 0) {
         if (common)    PML_LAUNCH((sweep_kernel<GRAD, SSIM, 0, false, true>), grid, blk, smem, st, pp);
         else if (emit) PML_LAUNCH((sweep_kernel<GRAD, SSIM, 0, true>), grid, blk, smem, st, pp);
@@ -282,6 +314,7 @@ int dispatch_S(int S, const PhotoParams& pp, int n_cta, int NT, int low_cells, c
 int run_loss(const pml_problem* p, void* ws, size_t ws_bytes, cudaStream_t st, bool grad) {
     int rc = validate(p, grad);
     if (rc != PML_OK) return rc;
+    NvtxRange nvtx_call(grad ? "pml_loss_forward_backward" : "pml_loss_forward");
     DeviceGuard guard(p->target);
     if (guard.foreign(p->pass[0].disp) || guard.foreign(p->losses) || guard.foreign(p->sources[0]) || guard.foreign(ws))
         return PML_ERR_INVALID;   // tensors of one call must live on one device
@@ -326,21 +359,7 @@ int run_loss(const pml_problem* p, void* ws, size_t ws_bytes, cudaStream_t st, b
         else      PML_LAUNCH(smooth_kernel<false>, dim3(pl.smooth_total), dim3(256), 0, st, sp);
     }
 
-    // 3. identity reprojection losses (automask), once for all passes; the sweep of the first frame pair also
-    //    leaves the window statistics of the target for the fused sweep
-    float4* tstat = (pl.sweep && ssim && pml::kSweepTstat) ? reinterpret_cast<float4*>(base + pl.off_tstat) : nullptr;
-    if (pl.n_id == 0 && tstat != nullptr) {   // no automask: a statistics-only pass of the same kernel
-        IdentityParams ip{};
-        ip.target = p->target; ip.src0 = p->target; ip.src1 = p->target;
-        ip.n_seg = sp.n_seg; ip.seg_size = sp.seg_size;
-        if (sg)
-            for (int j = 0; j < sg->n_seg; ++j) ip.target_c.p[j] = ip.src0_c.p[j] = ip.src1_c.p[j] = sg->target[j];
-        ip.out = nullptr; ip.tstat = tstat; ip.B = p->B; ip.H = p->H; ip.W = p->W; ip.S = 1;
-        ip.n_out = 1; ip.TH = knobs().id_th;
-        ip.n_strips = (p->W + kPrepTW - 1) / kPrepTW;
-        ip.n_chunks = (p->H + ip.TH - 1) / ip.TH;
-        PML_LAUNCH(identity_sweep_kernel<true>, dim3(ip.n_chunks * ip.n_strips, p->B), dim3(32), 0, st, ip);
-    }
+    // 3. identity reprojection losses (automask), once for all passes
     if (pl.n_id > 0 && pl.sweep) {
         for (int fa = 0; fa < p->S; fa += 2) {   // one launch per pair of source frames
             IdentityParams ip;
@@ -352,7 +371,6 @@ int run_loss(const pml_problem* p, void* ws, size_t ws_bytes, cudaStream_t st, b
                     ip.target_c.p[j] = sg->target[j]; ip.src0_c.p[j] = sg->sources[fa][j];
                     ip.src1_c.p[j] = sg->sources[fa + pair_n - 1][j];
                 }
-            ip.tstat = (fa == 0) ? tstat : nullptr;
             ip.out = identity; ip.B = p->B; ip.H = p->H; ip.W = p->W; ip.S = pair_n;
             ip.avg = (p->flags & PML_FLAG_AVG_REPROJ) ? 1 : 0;
             ip.n_out = pl.n_id; ip.plane_off = ip.avg ? 0 : fa; ip.accumulate = (ip.avg && fa > 0) ? 1 : 0;
@@ -386,7 +404,7 @@ int run_loss(const pml_problem* p, void* ws, size_t ws_bytes, cudaStream_t st, b
     pp.min_disp = (float)(1.0 / (double)p->max_depth);                                   // layers.py:21
     pp.disp_range = (float)(1.0 / (double)p->min_depth - 1.0 / (double)p->max_depth);     // layers.py:23
     pp.eps = p->eps; pp.seed = p->seed;
-    pp.target = p->target; pp.K = p->K; pp.invK = p->inv_K; pp.identity = identity; pp.tstat = tstat;
+    pp.target = p->target; pp.K = p->K; pp.invK = p->inv_K; pp.identity = identity;
     for (int f = 0; f < PML_MAX_SOURCES; ++f) { pp.src[f] = p->sources[f]; pp.T[f] = p->T[f]; }
     int low_cells = 0;
     for (int i = 0; i < p->n_pass; ++i) {
@@ -412,6 +430,7 @@ int run_loss(const pml_problem* p, void* ws, size_t ws_bytes, cudaStream_t st, b
             for (int f = 0; f < p->S; ++f) pp.src_c[f].p[j] = sg->sources[f][j];
         }
     if (p->prof_start) pml_event_record(p->prof_start, st);
+    NvtxRange nvtx_sweep("pml: fused sweep");
     if (pl.two_sweeps) {
         // More than two source frames (or per-frame weights): (1) forward sweep per frame pair -> reprojection losses,
         // (2) selection over all candidates, (3) forward + adjoint sweep per pair with that selection.
@@ -505,6 +524,7 @@ int pml_scale_grads(int32_t n_pass, int32_t B, int32_t S, const int32_t* hd, con
                     float* grad_T_out, pml_stream_t stream) {
     if (n_pass < 1 || n_pass > PML_MAX_PASSES || B < 1 || S < 1 || S > PML_MAX_SOURCES) return PML_ERR_INVALID;
     if (!hd || !wd || !grad_disp || !grad_disp_const || !grad_T || (!upstream && !upstream_total) || !grad_T_out) return PML_ERR_INVALID;
+    NvtxRange nvtx_call("pml_scale_grads");
     DeviceGuard guard(grad_T);
     pml::ScaleParams sp;
     sp.n_pass = n_pass; sp.B = B; sp.S = S;

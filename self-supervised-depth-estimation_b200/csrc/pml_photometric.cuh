@@ -43,7 +43,6 @@ struct PhotoParams {
     const float* invK;
     const float* T[PML_MAX_SOURCES];
     const float* identity;  // [B, n_id, H, W] identity reprojection losses (automask)
-    const float4* tstat;    // [B, H, W, 2] target window statistics (IdentityParams::tstat), warp-strip sweep with SSIM
     PassDev pass[PML_MAX_PASSES];
     int TW, TH, n_strips, n_chunks, cta_per_pass;   // cta_per_pass: work items (CTAs or warps) per pass
     int S;            // number of source frames (run-time copy of the template parameter)

@@ -44,10 +44,7 @@ struct IdentityParams {
     const float* target;
     const float* src0;
     const float* src1;     // == src0 when S == 1
-    float* out;            // [B, n_out, H, W], n_out = avg ? 1 : total source frames; null: statistics only
-    float4* tstat;         // [B, H, W, 2] x float4 or null: per window of the TARGET (mu_y[3], sigma_y[0] + C2 | sigma_y[1..2] + C2,
-                           // -, -): identical for every scale and source frame, so the fused sweep reads it instead of
-                           // re-deriving it four times per step (layers.py:238-243 on y)
+    float* out;            // [B, n_out, H, W], n_out = avg ? 1 : total source frames
     int B, H, W, S, avg;   // S: frames of THIS launch (1 or 2); more frames are swept pair by pair
     int n_out, plane_off;  // output planes per image, first plane written by this launch
     int accumulate;        // avg: add to what an earlier pair wrote
@@ -73,7 +70,7 @@ __device__ __forceinline__ void identity_sweep_body(const IdentityParams& p, con
     const float* __restrict__ s0_g = chunk_of(p.src0, p.src0_c, p.n_seg, p.seg_size, b, bl);
     const float* __restrict__ s1_g = chunk_of(p.src1, p.src1_c, p.n_seg, p.seg_size, b, bl);
     const int b3p = bl * 3 * plane;
-    float* out_b = (p.out != nullptr) ? p.out + ((size_t)b * p.n_out + p.plane_off) * plane : nullptr;
+    float* out_b = p.out + ((size_t)b * p.n_out + p.plane_off) * plane;
 
     float hy1[3], hy2[3], hyy1[3], hyy2[3];
     float2 hx1[3], hx2[3], hxx1[3], hxx2[3], hxy1[3], hxy2[3];
@@ -100,7 +97,6 @@ __device__ __forceinline__ void identity_sweep_body(const IdentityParams& p, con
                     float2 (&hxA)[3], float2 (&hxB)[3], float2 (&hxxA)[3], float2 (&hxxB)[3],
                     float2 (&hxyA)[3], float2 (&hxyB)[3]) {
         float2 ssim_sum = splat(0.f), l1_cur = splat(0.f);
-        float tmu[3] = {0.f, 0.f, 0.f}, tsg[3] = {0.f, 0.f, 0.f};
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const float yv = row.y[c];
@@ -121,9 +117,6 @@ __device__ __forceinline__ void identity_sweep_body(const IdentityParams& p, con
                 const float2 Sxy = add2(add2(hxyB[c], hxyA[c]), hxyn);
                 hyB[c] = hyn; hyyB[c] = hyyn; hxB[c] = hxn; hxxB[c] = hxxn; hxyB[c] = hxyn;
                 ssim_sum = add2(ssim_sum, ssim_pair_exact(Sx, Sxx, Sxy, Sy, Syy));
-                const float k9 = 1.0f / 9.0f;
-                tmu[c] = Sy * k9;
-                tsg[c] = fmaf(Syy, k9, -(tmu[c] * tmu[c])) + kSsimC2;
             }
         }
         // window row r-1 (trainer.py:527 / :523)
@@ -134,13 +127,7 @@ __device__ __forceinline__ void identity_sweep_body(const IdentityParams& p, con
                               fmaf(0.85f, ssim_sum.y * (1.0f / 3.0f), 0.15f * (l1_prev.y * (1.0f / 3.0f))));
             else rp = f2(l1_prev.x * (1.0f / 3.0f), l1_prev.y * (1.0f / 3.0f));
             const int pix = py * W + cx;
-            if (SSIM && p.tstat != nullptr) {
-                float4* tq = p.tstat + ((size_t)b * plane + pix) * 2;
-                tq[0] = make_float4(tmu[0], tmu[1], tmu[2], tsg[0]);
-                tq[1] = make_float4(tsg[1], tsg[2], 0.f, 0.f);
-            }
-            if (p.out == nullptr) {
-            } else if (p.avg) {
+            if (p.avg) {
                 const float v = ((p.S > 1) ? rp.x + rp.y : rp.x) * p.inv_total;   // trainer.py:565-566
                 out_b[pix] = p.accumulate ? out_b[pix] + v : v;
             } else {

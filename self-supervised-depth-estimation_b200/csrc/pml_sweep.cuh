@@ -33,14 +33,6 @@ constexpr int kSweepTW = 28;      // owned columns per strip
 constexpr int kSweepRingQ = 7;    // float4 per lane per ring slot
 constexpr int kSweepRingSlots = 4;   // rows r .. r-3 (the adjoint of row r-3 runs while row r's taps are in flight)
 constexpr int kSweepWarpFloats = 48 + 32 + kSweepRingSlots * kSweepRingQ * 4 * 32;   // P/IK, staging row, ring
-// Target window statistics (mu_y, sigma_y + C2 per channel) come precomputed from the identity sweep of prep_kernel
-// (IdentityParams::tstat): they are the same for all scales and source frames, and DRAM / L2 bandwidth is idle while
-// issue slots are the bottleneck (-DPML_NO_TSTAT restores the in-sweep evaluation for A/B measurements).
-#ifdef PML_NO_TSTAT
-constexpr bool kSweepTstat = false;
-#else
-constexpr bool kSweepTstat = true;
-#endif
 
 // ---- packed fp32x2 helpers (FFMA2 / FMUL2 / FADD2 on sm_100a) -----------------------------------
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
@@ -67,15 +59,6 @@ __device__ __forceinline__ const float* at(const float* base, int idx) {
 }
 __device__ __forceinline__ float* at(float* base, int idx) {
     return const_cast<float*>(at(static_cast<const float*>(base), idx));
-}
-// fire-and-forget float add to GLOBAL memory (RED.E.ADD.F32): atomicAdd on a generic pointer makes the compiler emit
-// the shared / local address-space fallbacks (25 instructions of dead code in the hot loop)
-__device__ __forceinline__ void red_add(float* addr, float v) {
-#ifdef PML_HOST_EMU
-    atomicAdd(addr, v);
-#else
-    asm volatile("red.global.add.f32 [%0], %1;" :: "l"(addr), "f"(v) : "memory");
-#endif
 }
 // MUFU.RCP (1 ulp); callers add the Newton step where the quotient decides something
 __device__ __forceinline__ float rcp_approx(float x) {
@@ -151,7 +134,7 @@ __device__ __noinline__ void sweep_flush_row(float* sG, float* gd_row, float h, 
             const float w = (jj0 == j ? 1.f - l : 0.f) + (jj1 == j ? l : 0.f);
             s = fmaf(w, sG[x - x0 + 2], s);
         }
-        if (s != 0.f) red_add(gd_row + j, s);
+        if (s != 0.f) atomicAdd(gd_row + j, s);
     }
     __syncwarp();
 }
@@ -267,18 +250,15 @@ sweep_kernel(const PhotoParams p) {
     const bool emit_any = EMIT && (mode != 2) && ((ps.depth != nullptr && fa == 0) || (ps.warped != nullptr));
 
     // ---- rolling state ---------------------------------------------------------------------------
-    constexpr bool TS = SSIM && kSweepTstat;
-    float hy1[TS ? 1 : 3], hy2[TS ? 1 : 3], hyy1[TS ? 1 : 3], hyy2[TS ? 1 : 3];
+    float hy1[3], hy2[3], hyy1[3], hyy2[3];
     float2 hx1[3], hx2[3], hxx1[3], hxx2[3], hxy1[3], hxy2[3];
     float2 hc1[GRAD ? 9 : 1], hc2[GRAD ? 9 : 1];
     float2 gP[GRAD ? 12 : 1];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        if (!TS) hy1[c] = hy2[c] = hyy1[c] = hyy2[c] = 0.f;
+        hy1[c] = hy2[c] = hyy1[c] = hyy2[c] = 0.f;
         hx1[c] = hx2[c] = hxx1[c] = hxx2[c] = hxy1[c] = hxy2[c] = splat(0.f);
     }
-    if (TS) hy1[0] = hy2[0] = hyy1[0] = hyy2[0] = 0.f;
-    const float4* __restrict__ ts_g = p.tstat;
 #pragma unroll
     for (int m = 0; m < (GRAD ? 9 : 1); ++m) hc1[m] = hc2[m] = splat(0.f);
 #pragma unroll
@@ -331,7 +311,7 @@ sweep_kernel(const PhotoParams p) {
     // both and overwrites the older one, so calling it with the two sets swapped on alternate rows
     // (loop unrolled by two below) rotates the window without a single register move.
     auto step = [&](const int r, const float (&yv)[3], const float (&dn)[4], float (&ynN)[3], float (&dnN)[4],
-                    float (&hyA)[TS ? 1 : 3], float (&hyB)[TS ? 1 : 3], float (&hyyA)[TS ? 1 : 3], float (&hyyB)[TS ? 1 : 3],
+                    float (&hyA)[3], float (&hyB)[3], float (&hyyA)[3], float (&hyyB)[3],
                     float2 (&hxA)[3], float2 (&hxB)[3], float2 (&hxxA)[3], float2 (&hxxB)[3],
                     float2 (&hxyA)[3], float2 (&hxyB)[3], float2 (&hcA)[GRAD ? 9 : 1], float2 (&hcB)[GRAD ? 9 : 1]) {
         // =================================== (A) warp row r ======================================
@@ -349,20 +329,13 @@ sweep_kernel(const PhotoParams p) {
         // identity losses / noise of the window row r-1 (used at the end of (B)); clamped so that the
         // early, unconditional loads stay inside the tensors
         const int py = r - 1;
-        float4 tsa = make_float4(0.f, 0.f, 0.f, 0.f), tsb = tsa;     // mu_y[0..2], sigma_y[0] + C2 | sigma_y[1..2] + C2
-        const int prow = clampi(py, 0, H - 1) * W + rx;   // every lane with a valid window has rx == cx
-        if (TS) {
-            const float4* tq = ts_g + 2 * (bp + prow);
-            tsa = __ldg(tq);
-            tsb = __ldg(tq + 1);
-        }
         float idv0 = 0.f, idv1 = 0.f, nzv0 = 0.f, nzv1 = 0.f;
         if (n_id > 0) {
-            const float* ic = at(id_g, bip + prow);
+            const float* ic = at(id_g, bip + clampi(py, 0, H - 1) * W + rx);
             idv0 = __ldg(ic);
             if (n_id > 1) idv1 = __ldg(at(ic, plane));
             if (nz_g != nullptr) {
-                const float* nc = at(nz_g, bip + prow);
+                const float* nc = at(nz_g, bip + clampi(py, 0, H - 1) * W + rx);
                 nzv0 = __ldg(nc);
                 if (n_id > 1) nzv1 = __ldg(at(nc, plane));
             }
@@ -500,7 +473,7 @@ sweep_kernel(const PhotoParams p) {
                     if (i0 + 1 <= hd - 1) { acc0 = fmaf(1.f - mu, g_d, acc0); acc1 = fmaf(mu, g_d, acc1); }
                     else acc0 += g_d;
                 } else if (col_owned && ps.grad_disp != nullptr) {
-                    red_add(at(ps.grad_disp, bp + qy * W + cx), g_d);
+                    atomicAdd(at(ps.grad_disp, bp + qy * W + cx), g_d);   // RED: fire and forget
                 }
             }
         }
@@ -553,32 +526,24 @@ sweep_kernel(const PhotoParams p) {
             for (int c = 0; c < 3; ++c) {
                 if (SSIM) {
                     const float yl = __shfl_up_sync(0xffffffffu, yv[c], 1), yr = __shfl_down_sync(0xffffffffu, yv[c], 1);
+                    const float hyn = yl + yv[c] + yr;
+                    const float hyyn = fmaf(yl, yl, fmaf(yv[c], yv[c], yr * yr));
                     const float2 xl = shfl_up2(xv[c]), xr = shfl_down2(xv[c]);
                     const float2 hxn = add2(add2(xl, xv[c]), xr);
                     const float2 hxxn = fma2(xl, xl, fma2(xv[c], xv[c], mul2(xr, xr)));
                     const float2 hxyn = fma2(xl, splat(yl), fma2(xv[c], splat(yv[c]), mul2(xr, splat(yr))));
+                    const float Sy = hyB[c] + hyA[c] + hyn;
+                    const float Syy = hyyB[c] + hyyA[c] + hyyn;
                     const float2 Sx = add2(add2(hxB[c], hxA[c]), hxn);
                     const float2 Sxx = add2(add2(hxxB[c], hxxA[c]), hxxn);
                     const float2 Sxy = add2(add2(hxyB[c], hxyA[c]), hxyn);
-                    hxB[c] = hxn; hxxB[c] = hxxn; hxyB[c] = hxyn;
-                    float my_, myyC1, syC2;
-                    if (TS) {   // window statistics of the target: precomputed once per step (IdentityParams::tstat)
-                        my_ = (c == 0) ? tsa.x : (c == 1 ? tsa.y : tsa.z);
-                        syC2 = (c == 0) ? tsa.w : (c == 1 ? tsb.x : tsb.y);
-                        myyC1 = fmaf(my_, my_, kSsimC1);
-                    } else {
-                        const float hyn = yl + yv[c] + yr;
-                        const float hyyn = fmaf(yl, yl, fmaf(yv[c], yv[c], yr * yr));
-                        const float Sy = hyB[TS ? 0 : c] + hyA[TS ? 0 : c] + hyn;
-                        const float Syy = hyyB[TS ? 0 : c] + hyyA[TS ? 0 : c] + hyyn;
-                        hyB[TS ? 0 : c] = hyn; hyyB[TS ? 0 : c] = hyyn;
-                        const float k9 = 1.0f / 9.0f;
-                        my_ = Sy * k9;
-                        const float myy = my_ * my_;
-                        myyC1 = myy + kSsimC1;
-                        syC2 = fmaf(Syy, k9, -myy) + kSsimC2;
-                    }
-                    ssim_sum = add2(ssim_sum, ssim_pair<GRAD>(Sx, Sxx, Sxy, my_, myyC1, syC2, pa[c], pb[c], pe[c]));
+                    hyB[c] = hyn; hyyB[c] = hyyn; hxB[c] = hxn; hxxB[c] = hxxn; hxyB[c] = hxyn;
+                    const float k9 = 1.0f / 9.0f;
+                    const float my_ = Sy * k9;
+                    const float myy = my_ * my_;
+                    const float sy_ = fmaf(Syy, k9, -myy);
+                    ssim_sum = add2(ssim_sum, ssim_pair<GRAD>(Sx, Sxx, Sxy, my_, myy + kSsimC1, sy_ + kSsimC2,
+                                                              pa[c], pb[c], pe[c]));
                 }
             }
             // trainer.py:527 (0.85 * SSIM.mean(1) + 0.15 * L1.mean(1)) or :523 (L1 only)
@@ -702,7 +667,7 @@ sweep_kernel(const PhotoParams p) {
             }
             if (col_owned && py >= y0 && py < y1) {
                 loss_acc += best;
-                if (COMMON || ps.argmin != nullptr) ps.argmin[bp + pix] = (uint8_t)best_i;   // COMMON: checked on the host
+                if (ps.argmin != nullptr) ps.argmin[bp + pix] = (uint8_t)best_i;
             }
         }
 

@@ -170,3 +170,24 @@ def test_depth_by_product_without_warped_images(emu_lib):
         assert common.rel_err(got["depth/%d" % s], ref["depth/%d" % s]) < 1e-5
         assert "color/-1/%d" % s not in got
     parity.check(got, opt, variant, inputs, outputs, seed, r32, r64)
+
+
+# ---- property test: random shapes, source counts and flags against the float64 oracle
+from hypothesis import HealthCheck, given, settings, strategies as st   # noqa: E402
+
+
+@settings(max_examples=10, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+@given(B=st.integers(1, 3), hq=st.integers(2, 5), wq=st.integers(4, 12), S=st.integers(1, 4),
+       flags=st.sampled_from([{}, dict(no_ssim=True), dict(avg_reprojection=True), dict(disable_automasking=True),
+                              dict(avg_reprojection=True, disable_automasking=True)]),
+       n_scales=st.integers(1, 4), style=st.sampled_from(["kitti", "uniform", "oof", "constant"]), seed=st.integers(0, 10 ** 6))
+def test_random_configurations_match_the_oracle(emu_lib, B, hq, wq, S, flags, n_scales, style, seed):
+    H, W = 8 * hq, 8 * wq                      # multiples of 8: every scale 0..3 has an integer size
+    sources = (-1, 1, -2, 2)[:S]
+    opt = synthetic.make_options(H, W, batch_size=B, scales=list(range(n_scales)), **flags)
+    inputs, outputs = synthetic.make_batch(B, H, W, sources=sources, seed=seed, style=style, scales=opt.scales)
+    got = common.run_product(opt, inputs, outputs, "trainer", device="cpu", noise_seed=seed % 1000, sources=sources)
+    degenerate = (style == "constant") or (flags.get("avg_reprojection") and flags.get("disable_automasking")) or \
+        (flags.get("disable_automasking") and S == 1)
+    parity.check(got, opt, "trainer", inputs, outputs, seed % 1000, sources=sources, degenerate=bool(degenerate),
+                 loss_tol=parity.LOSS_TOL_SMALL)
