@@ -11,8 +11,9 @@ scales 0-3, automask + SSIM, fp32.  metric = target pixels (B*H*W) processed per
 ours:       value    = CUDA-graph replay of the step with inputs resident in HBM, rotating over
                        input sets whose total exceeds L2 so every step starts cold; CUDA events.
             e2e      = the reference-facing drop-in call (trainer_hooks.ingest_colors + Trainer.generate_images_pred
-                       + compute_losses + backward), inputs in pinned HOST memory, H2D copies and the D2H read of
-                       the loss inside the timed region.  The host holds what the image decoder delivers -- uint8
+                       + compute_losses + backward) in its opt-in CUDA-graph mode (trainer_hooks.GraphedLoss), inputs
+                       in pinned HOST memory, H2D copies and the D2H read of the loss inside the timed region
+                       (e2e_eager: the same step through the plain eager drop-ins).  The host holds what the image decoder delivers -- uint8
                        scale-0 frames -- and ingest_colors builds the fp32 colour pyramid on the device, bit-exact
                        with the reference's PIL + ToTensor preprocessing (mono_dataset.py:99-111).
             e2e_fp32_pyramid = the same loop with the host holding the reference DataLoader's fp32 pyramids
@@ -353,9 +354,88 @@ def run_ours(args, rank, world, dev):
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4, "steps": Ke,
                 "ms_per_step": round(t.item() / Ke * 1e3, 4), "copies_declared": True, "host_input": mode, "api": api}
 
+    def e2e_graph_arm():
+        """The same step through trainer_hooks.GraphedLoss: ingest + fused loss captured once per slot as a CUDA
+        graph on static input slots; per step one H2D copy into the slot (copy stream), one graph launch, the
+        eager backward (one kernel) and loss.item().  Two slots: the upload of step i+1 overlaps step i."""
+        from ssde_b200 import hostio
+        o2 = SimpleNamespace(**vars(opt))
+        o2.pml_sources, o2.pml_variant, o2.pml_emit_depth = srcs, "trainer", "scale0"
+        ns = SimpleNamespace(opt=o2, device=dev, num_scales=len(opt.scales))
+        frames = [0] + list(srcs)
+        host = []
+        for (i, o) in sets:
+            hb = {"color_u8": torch.stack([(i[("color", f, 0)].permute(0, 2, 3, 1) * 255.0).round().clamp(0, 255)
+                                           .to(torch.uint8) for f in frames], 0).contiguous()}
+            hb.update({k: v for k, v in i.items() if not (isinstance(k, tuple) and k[0] == "color")})
+            hb.update({k: v for k, v in o.items() if k[0] in ("disp", "cam_T_cam")})
+            host.append(hostio.PinnedBatch(hb))
+        runner = trainer_hooks.GraphedLoss(ns)
+        copy_stream = torch.cuda.Stream(device=dev)
+        main_stream = torch.cuda.current_stream(dev)
+        slots = []
+        for s in range(2):
+            d, arena = host[0].upload(dev)
+            torch.cuda.synchronize()
+            inp = {k: v for k, v in d.items() if not (isinstance(k, tuple) and k[0] in ("disp", "cam_T_cam"))}
+            out = {k: v.requires_grad_(True) for k, v in d.items() if isinstance(k, tuple) and k[0] in ("disp", "cam_T_cam")}
+            slot = runner.capture(inp, out)
+            done = torch.cuda.Event()
+            done.record(main_stream)
+            slots.append((slot, arena, out, done))
+
+        def upload(hb, s):
+            slot, arena, out, done = slots[s]
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done)          # the previous step on this slot has finished with it
+                hb.upload_into(arena)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return ev
+
+        def compute(s, ev):
+            slot, arena, out, done = slots[s]
+            main_stream.wait_event(ev)
+            for v in out.values():
+                v.grad = None
+            losses = slot.replay()
+            losses["loss"].backward()
+            done.record(main_stream)
+            return losses["loss"]
+
+        def run_steps(n):
+            nxt = upload(host[0], 0)
+            last = None
+            for i in range(n):
+                cur = nxt
+                if i + 1 < n:
+                    nxt = upload(host[(i + 1) % len(host)], (i + 1) % 2)
+                last = compute(i % 2, cur).item()   # D2H read of the step's result
+            return last
+
+        Ke = max(3, min(K, 100))
+        run_steps(5)
+        barrier()
+        t0 = time.perf_counter()
+        run_steps(Ke)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return {"value": round(world * n_pix * Ke / t.item() / 1e6, 2), "unit": UNIT, "h2d_bytes_per_step": int(host[0].nbytes),
+                "d2h_bytes_per_step": 4, "steps": Ke, "ms_per_step": round(t.item() / Ke * 1e3, 4), "copies_declared": True,
+                "host_input": "u8",
+                "api": "trainer_hooks.GraphedLoss (opt-in CUDA-graph mode of the drop-in pair generate_images_pred + compute_losses, "
+                       "uint8 ingest inside the graph): per step one H2D copy of the pinned host arena (hostio.PinnedBatch) into a "
+                       "static slot on a copy stream, slot.replay(), loss.backward(), loss.item(); two slots, upload of step i+1 "
+                       "overlapped with step i"}
+
+    e2e_eager = None
     if not args.no_e2e:
-        e2e = e2e_arm("u8")
+        e2e_eager = e2e_arm("u8")
         e2e_fp32 = e2e_arm("fp32")
+        e2e = e2e_graph_arm()
 
     extra = {}
     if not args.no_extra:
@@ -368,7 +448,7 @@ def run_ours(args, rank, world, dev):
            "ms_per_step": round(ms_total / K, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
            "config": config_dict(args),
-           "clocks": clk, "e2e": e2e, "e2e_fp32_pyramid": e2e_fp32, "gpu_launches": kernels_per_step * K, "roofline": roofline}
+           "clocks": clk, "e2e": e2e, "e2e_eager": e2e_eager, "e2e_fp32_pyramid": e2e_fp32, "gpu_launches": kernels_per_step * K, "roofline": roofline}
     res["roofline_issue"] = roofline_issue
     res.update(extra)
     return res
@@ -517,8 +597,10 @@ def ddp_step_arm(dev, rank, world, barrier, steps, batch=8, height=320, width=10
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item() / steps
-    ms = timed(True)
     ms_nets = timed(False)
+    ms = timed(True)
+    ms = min(ms, timed(True))
+    ms_nets = min(ms_nets, timed(False))     # bracket the loss arm: clocks / cuDNN autotuning drift between runs
     del model, nets, optim
     torch.cuda.empty_cache()
     return {"workload": "configs[2] training step: mono+stereo 320x1024, batch %d per GPU, stock ResNet-18 depth+pose networks, "

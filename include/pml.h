@@ -34,7 +34,7 @@ extern "C" {
  * (predictive mask), pml_upsample_*, pml_bce_ones_*, pml_pyramid_u8; 3 = PML_MAX_SOURCES 4 -> 8 (array sizes in
  * pml_problem) and pml_problem.loss_vector; 4 = pml_problem.loss_total / loss_total_div (the mean over scales,
  * trainer.py:621, written by the library), pml_problem.segments (per-timestep tensors of the sequence trainer consumed
- * in place), pml_scale_grads takes the upstream of the total, pml_selection_masks, pml_disp_head_*, PML_FLAG_KERNEL_CTA.
+ * in place), pml_problem.seed_device, pml_scale_grads takes the upstream of the total, pml_selection_masks, pml_disp_head_*, PML_FLAG_KERNEL_CTA.
  * The Python binding refuses a library of another version. */
 #define PML_ABI_VERSION 4
 #define PML_MAX_SOURCES 8 /* source frames per target, e.g. (-1, 1, "s") = 3; BASELINE config 5 sweeps 2/4/8 */
@@ -123,6 +123,8 @@ typedef struct pml_problem {
     float loss_total_div;   /* divisor of loss_total; 0 is read as n_pass */
     int32_t reserved2;
     const pml_segments* segments; /* nullable, see pml_segments */
+    const uint64_t* seed_device;  /* nullable DEVICE pointer: *seed_device is xor'ed into `seed` by the kernels, so a captured
+                                     CUDA graph draws fresh tie-break noise on every replay (the caller advances the value) */
 } pml_problem;
 
 int pml_abi_version(void);

@@ -46,7 +46,7 @@ class PmlProblem(Structure):
                 ("losses", c_void_p), ("grad_T", c_void_p), ("grad_disp_const", c_void_p),
                 ("prof_start", c_void_p), ("prof_stop", c_void_p), ("loss_vector", c_void_p),
                 ("loss_total", c_void_p), ("loss_total_div", c_float), ("reserved2", c_int32),
-                ("segments", POINTER(PmlSegments))]
+                ("segments", POINTER(PmlSegments)), ("seed_device", c_void_p)]
 
 
 class PmlError(RuntimeError):

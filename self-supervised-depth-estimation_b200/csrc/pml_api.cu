@@ -403,7 +403,7 @@ int run_loss(const pml_problem* p, void* ws, size_t ws_bytes, cudaStream_t st, b
     pp.B = p->B; pp.H = p->H; pp.W = p->W; pp.n_pass = p->n_pass; pp.flags = p->flags;
     pp.min_disp = (float)(1.0 / (double)p->max_depth);                                   // layers.py:21
     pp.disp_range = (float)(1.0 / (double)p->min_depth - 1.0 / (double)p->max_depth);     // layers.py:23
-    pp.eps = p->eps; pp.seed = p->seed;
+    pp.eps = p->eps; pp.seed = p->seed; pp.seed_dev = reinterpret_cast<const unsigned long long*>(p->seed_device);
     pp.target = p->target; pp.K = p->K; pp.invK = p->inv_K; pp.identity = identity;
     for (int f = 0; f < PML_MAX_SOURCES; ++f) { pp.src[f] = p->sources[f]; pp.T[f] = p->T[f]; }
     int low_cells = 0;

@@ -37,6 +37,7 @@ struct PhotoParams {
     unsigned flags;
     float min_disp, disp_range, eps;
     unsigned long long seed;
+    const unsigned long long* seed_dev;   // optional: xor'ed into seed on the device (CUDA-graph replays with fresh noise)
     const float* target;
     const float* src[PML_MAX_SOURCES];
     const float* K;
@@ -409,7 +410,7 @@ photometric_kernel(const PhotoParams p) {
                 float nz[4] = {0.f, 0.f, 0.f, 0.f};
                 if (ps.noise == nullptr) {
                     size_t lin = (size_t)b * plane + pix;
-                    philox_normal4(p.seed, (uint32_t)lin, (uint32_t)(lin >> 32), (uint32_t)pass_i, nz);
+                    philox_normal4(p.seed_dev ? (p.seed ^ __ldg(p.seed_dev)) : p.seed, (uint32_t)lin, (uint32_t)(lin >> 32), (uint32_t)pass_i, nz);
                 }
                 for (int i = 0; i < n_id; ++i) {
                     size_t off = ((size_t)b * n_id + i) * plane + pix;

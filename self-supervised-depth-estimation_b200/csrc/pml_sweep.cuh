@@ -561,8 +561,11 @@ sweep_kernel(const PhotoParams p) {
             const float m_rp = avg ? (two ? (rp.x + rp.y) * 0.5f : rp.x) : (two ? fminf(rp.x, rp.y) : rp.x);
             const bool close = (n_id > 1 && fabsf(idv0 - idv1) < 1.4e-4f) || (fabsf(m_id - m_rp) < 1.4e-4f);
             if (__any_sync(0xffffffffu, close && p_valid))
-                philox2_normal2((uint32_t)p.seed ^ ((uint32_t)(p.seed >> 32) * 0x9E3779B9u),
+            {
+                const unsigned long long sd = p.seed_dev ? (p.seed ^ __ldg(p.seed_dev)) : p.seed;
+                philox2_normal2((uint32_t)sd ^ ((uint32_t)(sd >> 32) * 0x9E3779B9u),
                                 (uint32_t)(bp + py * W + cx), (uint32_t)pass_i, nzv0, nzv1);
+            }
         }
         float2 wgt = splat(0.f);
         if (mode == 1) {
@@ -596,7 +599,8 @@ sweep_kernel(const PhotoParams p) {
                         n0 = __ldg(at(nz_g, o));
                         if (i + 1 < n_sel) n1 = __ldg(at(nz_g, o + plane));
                     } else {
-                        philox2_normal2((uint32_t)p.seed ^ ((uint32_t)(p.seed >> 32) * 0x9E3779B9u), (uint32_t)(bp + pix),
+                        const unsigned long long sd = p.seed_dev ? (p.seed ^ __ldg(p.seed_dev)) : p.seed;
+                        philox2_normal2((uint32_t)sd ^ ((uint32_t)(sd >> 32) * 0x9E3779B9u), (uint32_t)(bp + pix),
                                         (uint32_t)pass_i + 0x10000u * (uint32_t)(i >> 1), n0, n1);
                     }
                     const float c0 = fmaf(n0, kTieNoise, __ldg(at(id_g, o)));

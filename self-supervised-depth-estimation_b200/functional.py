@@ -148,6 +148,8 @@ class _PhotometricLoss(torch.autograd.Function):
         kshape = (seg_size if n_seg else B, 4, 4)
 
         prob.seed = cfg.get("seed", 0)
+        sd = cfg.get("seed_device")
+        prob.seed_device = sd.data_ptr() if sd is not None else None
         if n_seg:
             sg = pl.segs
             for j in range(n_seg):
@@ -276,39 +278,43 @@ class _PhotometricLoss(torch.autograd.Function):
             raise RuntimeError("libpml photometric-loss gradients were already consumed in place by a previous "
                                "backward(); re-run the forward pass instead of retain_graph")
         ctx.consumed = True
-        lib = get_library()
-        pl = ctx.plan
-        n_pass, S, B, has_fw, stream = ctx.dims
-        if g_vec is not None:
-            g_vec = g_vec.contiguous().to(torch.float32)
-        if g_total is not None:
-            g_total = g_total.contiguous().to(torch.float32)
-        small = ctx.small
-        so = pl.small_off
-        gT_out = torch.empty((S, B, 4, 4), device=small.device, dtype=torch.float32)
-        gdisps, gfws = ctx.gdisps, ctx.gfws
-        for i in range(n_pass):
-            pl.gptrs[i] = gdisps[i].data_ptr()
-        sp = small.data_ptr()
-        lib.check(lib.pml_scale_grads(n_pass, B, S, pl.hd, pl.wd, pl.gptrs, sp + 4 * so["gconst"], sp + 4 * so["gT"],
-                                      _ptr(g_vec), _ptr(g_total), pl.prob.loss_total_div, _ptr(gT_out),
-                                      ctypes.c_void_p(stream)), "pml_scale_grads")
-        need = ctx.needs_input_grad[1:]
-        # hand the gradient buffers over without keeping a reference: AccumulateGrad then adopts them as
+        grads = _scale_gradients(ctx.plan, ctx.dims, ctx.gdisps, ctx.small, ctx.gfws, g_vec, g_total, ctx.needs_input_grad[1:])
+        # the gradient buffers are handed over without keeping a reference: AccumulateGrad then adopts them as
         # the leaves' .grad instead of cloning them (one 5.9 MB copy kernel per scale-0 disparity otherwise)
         ctx.gdisps = ctx.gfws = ctx.small = ctx.garena = None
-        grads: List[Optional[torch.Tensor]] = [None]
-        for i in range(n_pass):
-            grads.append(gdisps[i] if need[i] else None)
-        for f in range(S):
-            grads.append(gT_out[f] if need[n_pass + f] else None)
-        if gfws:   # d loss_s / d mask_s, scaled by the incoming gradient
-            up = (g_vec if g_vec is not None else 0) + (g_total / pl.prob.loss_total_div if g_total is not None else 0)
-            for i, gw in enumerate(gfws):
-                grads.append(gw.mul_(up[i] if up.dim() else up) if need[n_pass + S + i] else None)
-        del gdisps, gfws
-        grads += [None] * (n_in - len(grads))
-        return tuple(grads)
+        return (None,) + tuple(grads) + (None,) * (n_in - 1 - len(grads))
+
+
+def _scale_gradients(pl, dims, gdisps, small, gfws, g_vec, g_total, need):
+    """Backward of the fused node: the sweep already left d loss_s / d (disp_s, T_f) in ``gdisps`` / ``small``;
+    one launch (pml_scale_grads) multiplies them by the incoming gradients in place.  -> grads for
+    disps | Ts | frame weights."""
+    lib = get_library()
+    n_pass, S, B, has_fw, _ = dims
+    # autograd runs a node's backward on the stream of its forward; a replayed graph runs on the current stream
+    stream = torch.cuda.current_stream(small.device).cuda_stream if small.is_cuda else 0
+    if g_vec is not None:
+        g_vec = g_vec.contiguous().to(torch.float32)
+    if g_total is not None:
+        g_total = g_total.contiguous().to(torch.float32)
+    so = pl.small_off
+    gT_out = torch.empty((S, B, 4, 4), device=small.device, dtype=torch.float32)
+    for i in range(n_pass):
+        pl.gptrs[i] = gdisps[i].data_ptr()
+    sp = small.data_ptr()
+    lib.check(lib.pml_scale_grads(n_pass, B, S, pl.hd, pl.wd, pl.gptrs, sp + 4 * so["gconst"], sp + 4 * so["gT"],
+                                  _ptr(g_vec), _ptr(g_total), pl.prob.loss_total_div, _ptr(gT_out),
+                                  ctypes.c_void_p(stream)), "pml_scale_grads")
+    grads: List[Optional[torch.Tensor]] = []
+    for i in range(n_pass):
+        grads.append(gdisps[i] if need[i] else None)
+    for f in range(S):
+        grads.append(gT_out[f] if need[n_pass + f] else None)
+    if gfws:   # d loss_s / d mask_s, scaled by the incoming gradient
+        up = (g_vec if g_vec is not None else 0) + (g_total / pl.prob.loss_total_div if g_total is not None else 0)
+        for i, gw in enumerate(gfws):
+            grads.append(gw.mul_(up[i] if up.dim() else up) if need[n_pass + S + i] else None)
+    return grads
 
 
 def photometric_loss(target, sources: Sequence, K, inv_K, Ts: Sequence[torch.Tensor],
@@ -318,7 +324,7 @@ def photometric_loss(target, sources: Sequence, K, inv_K, Ts: Sequence[torch.Ten
                      noise: Optional[Sequence[torch.Tensor]] = None, seed: int = 0,
                      emit_depth: Sequence[int] = (), emit_warped: Sequence[int] = (), prof_events=None,
                      frame_weights: Optional[Sequence[torch.Tensor]] = None, kernel: str = "sweep",
-                     total_div: Optional[float] = None):
+                     total_div: Optional[float] = None, seed_device: Optional[torch.Tensor] = None):
     """Fused view synthesis + photometric loss for ``len(disps)`` scales sharing one image set.
 
     Returns a dict: ``loss`` [n_pass] (differentiable w.r.t. ``disps`` and ``Ts``; element s is
@@ -335,7 +341,9 @@ def photometric_loss(target, sources: Sequence, K, inv_K, Ts: Sequence[torch.Ten
     ``frame_weights`` (one [B,S,H,W] tensor per scale, differentiable) is the ``--predictive_mask``
     ablation (trainer.py:571-579): the mask, already resized to H x W, multiplies each frame's
     reprojection loss before the mean / min; like the reference it needs ``disable_automasking``.
-    ``kernel="cta"`` runs the first-generation CTA-strip kernel (testing: an independent cross-check)."""
+    ``kernel="cta"`` runs the first-generation CTA-strip kernel (testing: an independent cross-check).
+    ``seed_device``: int64 tensor [1] on the device whose value is xor'ed into ``seed`` by the kernels (a captured
+    CUDA graph then draws fresh tie-break noise on every replay)."""
     n_pass, S = len(disps), len(sources)
     if not (1 <= n_pass <= PML_MAX_PASSES):
         raise ValueError("1..%d scales per call" % PML_MAX_PASSES)
@@ -379,7 +387,7 @@ def photometric_loss(target, sources: Sequence, K, inv_K, Ts: Sequence[torch.Ten
                smooth_weights=[float(w) for w in smooth_weights], has_noise=use_noise, seed=int(seed) & (2 ** 64 - 1),
                emit_depth=tuple(emit_depth), emit_warped=tuple(emit_warped), prof_events=prof_events,
                has_fw=frame_weights is not None, images=images,
-               total_div=float(total_div) if total_div else None)
+               total_div=float(total_div) if total_div else None, seed_device=seed_device)
     tensors = list(disps) + list(Ts) + (list(frame_weights) if frame_weights is not None else [])
     outs = _PhotometricLoss.apply(cfg, *tensors)
     am = outs[3]

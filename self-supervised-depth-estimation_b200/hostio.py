@@ -41,3 +41,7 @@ class PinnedBatch:
     def upload(self, device) -> Tuple[Dict, torch.Tensor]:
         dev_arena = self.arena.to(device, non_blocking=True)
         return {k: dev_arena[o:o + n].view(dt).view(shape) for (k, o, n, dt, shape) in self.layout}, dev_arena
+
+    def upload_into(self, dev_arena: torch.Tensor) -> None:
+        """Refill a device arena obtained from an earlier :meth:`upload` in place (static slots of a CUDA graph)."""
+        dev_arena.copy_(self.arena, non_blocking=True)

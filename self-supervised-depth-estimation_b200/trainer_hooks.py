@@ -104,7 +104,9 @@ def _run_fused(self, inputs, outputs):
             noise[s] = torch.randn([B, n_id, h, w]).to(self.device)
     seed = 0
     if automask and noise_mode != "host":
-        seed = int(torch.empty((), dtype=torch.int64).random_().item())
+        seed = _opt(opt, "pml_seed", None)
+        if seed is None:
+            seed = int(torch.empty((), dtype=torch.int64).random_().item())
 
     res = {"loss": {}, "terms": {}, "argmin": {}, "n_id": n_id, "total": None, "argmin_all": None, "sources": sources}
     for group in groups:
@@ -165,9 +167,9 @@ def _run_fused(self, inputs, outputs):
             disable_automasking=opt.disable_automasking, avg_reprojection=opt.avg_reprojection,
             noise=[noise[s] for s in group] if noise else None, seed=seed + 7919 * scales.index(group[0]),
             emit_depth=ed, emit_warped=ew, frame_weights=fws if pmask else None,
-            kernel=_opt(opt, "pml_kernel", "sweep"), total_div=len(scales))
+            kernel=_opt(opt, "pml_kernel", "sweep"), total_div=len(scales), seed_device=_opt(opt, "pml_seed_device", None))
         if len(groups) == 1 and not pmask:
-            res["total"], res["argmin_all"] = out["total"], out["argmin_all"]
+            res["total"], res["argmin_all"], res["loss_vec"] = out["total"], out["argmin_all"], out["loss"]
         for i, s in enumerate(group):
             res["loss"][s] = out["loss"][i] + bces[i] if pmask else out["loss"][i]
             res["terms"][s] = out["terms"][i]
@@ -292,6 +294,155 @@ def materialize_logged_outputs(self, inputs, outputs):
 class _Shim:
     def __init__(self, opt, device, num_scales):
         self.opt, self.device, self.num_scales = opt, device, num_scales
+
+
+class GraphedLoss:
+    """Opt-in CUDA-graph execution of the drop-in pair ``generate_images_pred`` + ``compute_losses``.
+
+    The forward of the fused loss (input pyramid when uint8 frames are given, identity / smoothness sweeps, the
+    fused sweep with its adjoint, the reductions, ``outputs[("depth", 0, 0)]``) is captured once per slot on
+    STATIC input tensors and replayed with one ``cudaGraphLaunch`` per step; the backward stays the single eager
+    ``pml_scale_grads`` launch.  Host cost per step: one graph launch instead of ~10 kernel launches, ~15
+    allocations and the Python around them.
+
+        runner = GraphedLoss(trainer_like)                 # .opt, .device, .num_scales like the reference Trainer
+        slot = runner.capture(inputs, outputs)             # these tensors become the static slot: refill them IN PLACE
+        ...
+        losses = slot.replay()                             # {"loss", "loss/{s}"}; differentiable w.r.t. the slot's
+        losses["loss"].backward()                          #   outputs[("disp", s)] / ("cam_T_cam", 0, f) tensors
+        # or, with tensors that change address every step (network outputs):
+        losses = runner(inputs, outputs)                   # copies them into slot 0 (one multi-tensor copy), replays
+
+    Restrictions: one group of scales (no v1_multiscale / posecnn / predictive mask), in-kernel tie-break noise
+    (a device-side counter advances the Philox seed on every replay), fixed shapes per slot."""
+
+    class Slot:
+        def __init__(self, runner, inputs, outputs):
+            self.runner, self.inputs, self.outputs = runner, inputs, outputs
+            self.graph, self.node, self.vec, self.total, self.static_diff = None, None, None, None, None
+
+        def replay(self, diff_tensors=None):
+            if diff_tensors is None:
+                diff_tensors = self.static_diff
+            vec, total = _GraphedFn.apply(self, *diff_tensors)
+            losses = {"loss/{}".format(s): vec[i] for i, s in enumerate(self.runner.scales)}
+            losses["loss"] = total
+            return losses
+
+    def __init__(self, trainer_like):
+        self.owner = trainer_like
+        opt = trainer_like.opt
+        if opt.v1_multiscale and _opt(opt, "pml_variant", "trainer") != "fusion":
+            raise ValueError("GraphedLoss: v1_multiscale evaluates every scale by its own call; not supported")
+        if _opt(opt, "pose_model_type", "") == "posecnn" or (_opt(opt, "predictive_mask", False) and opt.disable_automasking):
+            raise ValueError("GraphedLoss: posecnn / predictive_mask need eager glue around the fused call; not supported")
+        self.scales = list(opt.scales)
+        self.sources = list(_opt(opt, "pml_sources", [-1, 1]))
+        self.slots = []
+
+    def _diff_keys(self):
+        return [("disp", s) for s in self.scales] + [("cam_T_cam", 0, f) for f in self.sources if f != "s"]
+
+    def capture(self, inputs, outputs):
+        from types import SimpleNamespace
+        own = self.owner
+        dev = own.device
+        o = SimpleNamespace(**vars(own.opt))
+        o.pml_noise, o.pml_emit_warped, o.pml_emit_selection = "philox", False, False
+        seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        o.pml_seed_device, o.pml_seed = seed_dev, int(torch.empty((), dtype=torch.int64).random_().item())
+        shim = _Shim(o, dev, own.num_scales)
+        slot = GraphedLoss.Slot(self, inputs, outputs)
+        slot.seed_dev = seed_dev
+        slot.static_diff = [outputs[k] for k in self._diff_keys()]
+        frames = [0] + [f for f in self.sources]
+
+        def body():
+            inp = dict(inputs)
+            if "color_u8" in inp or ("color_u8", 0) in inp:
+                ingest_colors(inp, frames, own.num_scales, device=dev)
+            out = dict(outputs)
+            for k in self._diff_keys():
+                out[k] = outputs[k].detach().requires_grad_(True)
+            res = _run_fused(shim, inp, out)
+            seed_dev.add_(0x9E3779B97F4A7C15 - (1 << 64))      # next replay: another Philox stream
+            return res, out
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):          # warm-up: module load, launch plans, allocator
+                body()
+            side.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                res, out = body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        if res["total"] is None:
+            raise ValueError("GraphedLoss: this configuration does not run as one fused call")
+        slot.graph, slot.res, slot.captured_out = g, res, out
+        slot.node = res["total"].grad_fn      # the _PhotometricLoss node of the capture: owns the static gradient buffers
+        slot.vec, slot.total = res["loss_vec"].detach(), res["total"].detach()
+        if ("depth", 0, 0) in out:
+            outputs[("depth", 0, 0)] = out[("depth", 0, 0)]
+        for s in self.scales:
+            outputs[("argmin", s)] = res["argmin"][s]
+        self.slots.append(slot)
+        return slot
+
+    def __call__(self, inputs, outputs):
+        """Drop-in form: ``inputs`` / ``outputs`` of this step are copied into slot 0 (captured on first use)."""
+        if not self.slots:
+            static_in = {k: v.detach().clone() for k, v in inputs.items() if isinstance(v, torch.Tensor) and v.is_cuda}
+            static_out = {k: outputs[k].detach().clone() for k in self._diff_keys()}
+            self.capture(static_in, static_out)
+        slot = self.slots[0]
+        dst = [v for k, v in slot.inputs.items()]
+        src = [inputs[k] for k in slot.inputs]
+        pairs = [(d, s_) for d, s_ in zip(dst, src) if d.data_ptr() != s_.data_ptr()]
+        if pairs:
+            torch._foreach_copy_([d for d, _ in pairs], [s_.detach() for _, s_ in pairs])
+        losses = slot.replay([outputs[k] for k in self._diff_keys()])
+        for k in (("depth", 0, 0),):
+            if k in slot.outputs:
+                outputs[k] = slot.outputs[k]
+        for s in self.scales:
+            outputs[("argmin", s)] = slot.outputs[("argmin", s)]
+        return losses
+
+
+class _GraphedFn(torch.autograd.Function):
+    """Replay of a captured forward.  inputs: the slot, then the caller's disparities and poses (copied into the
+    slot's static tensors unless they ARE those tensors)."""
+
+    @staticmethod
+    def forward(ctx, slot, *tensors):
+        pairs = [(d, t) for d, t in zip(slot.static_diff, tensors) if d.data_ptr() != t.data_ptr()]
+        if pairs:
+            torch._foreach_copy_([d for d, _ in pairs], [t.detach() for _, t in pairs])
+        slot.graph.replay()
+        ctx.slot = slot
+        ctx.leaf = [t.is_leaf for t in tensors]
+        ctx.set_materialize_grads(False)
+        # the static result buffers are overwritten by the next replay: hand out copies (n_pass + 1 floats)
+        return slot.vec.clone(), slot.total.clone()
+
+    @staticmethod
+    def backward(ctx, g_vec, g_total):
+        slot = ctx.slot
+        node = slot.node
+        if g_vec is None and g_total is None:
+            return (None,) * (1 + len(ctx.leaf))
+        runner = slot.runner
+        n_pass = len(runner.scales)
+        pose = [f != "s" for f in runner.sources]              # the stereo pose is an input, not a prediction
+        need_in = list(ctx.needs_input_grad[1:])
+        it = iter(need_in[n_pass:])
+        need = need_in[:n_pass] + [bool(next(it)) if p else False for p in pose]
+        grads = _F._scale_gradients(node.plan, node.dims, node.gdisps, node.small, [], g_vec, g_total, need)
+        grads = grads[:n_pass] + [g for g, p in zip(grads[n_pass:], pose) if p]
+        # static buffers: a leaf would adopt the buffer itself as its .grad and see it overwritten by the next replay
+        grads = [g.clone() if (g is not None and leaf) else g for g, leaf in zip(grads, ctx.leaf)]
+        return (None,) + tuple(grads)
 
 
 DEPTH_METRIC_NAMES = ["de/abs_rel", "de/sq_rel", "de/rms", "de/log_rms", "da/a1", "da/a2", "da/a3"]   # trainer.py:121-122

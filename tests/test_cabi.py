@@ -44,7 +44,7 @@ def test_struct_layout_matches_header():
     assert _cabi.PmlProblem.seed.offset == 40
     assert _cabi.PmlProblem.target.offset == 48
     assert _cabi.PmlProblem.passes.offset == 48 + 8 * (1 + 8 + 2 + 8)
-    assert ctypes.sizeof(_cabi.PmlProblem) == _cabi.PmlProblem.passes.offset + 8 * ctypes.sizeof(_cabi.PmlPass) + 48 + 24
+    assert ctypes.sizeof(_cabi.PmlProblem) == _cabi.PmlProblem.passes.offset + 8 * ctypes.sizeof(_cabi.PmlPass) + 48 + 32
 
 
 def test_argument_validation_without_gpu(lib):

@@ -116,6 +116,58 @@ def test_pose_gradient_with_kink_pixels_weighed_out(cuda_lib, H, W, seed, style)
     print(rep)
 
 
+def test_graphed_loss_matches_the_eager_dropins(cuda_lib):
+    """trainer_hooks.GraphedLoss (CUDA-graph replay of generate_images_pred + compute_losses on static slots)
+    gives the eager drop-ins' losses, selection and gradients, step after step, with uint8 ingest in the graph."""
+    from types import SimpleNamespace
+    from ssde_b200 import trainer_hooks, hostio
+    dev = torch.device("cuda")
+    B, H, W = 2, 96, 320
+    opt = synthetic.make_options(H, W, batch_size=B)
+    opt.pml_sources, opt.pml_variant, opt.pml_emit_depth = [-1, 1], "trainer", "scale0"
+    ns = SimpleNamespace(opt=opt, device=dev, num_scales=4)
+    frames = [0, -1, 1]
+    batches = []
+    for seed in (1, 2, 3):
+        i, o = synthetic.make_batch(B, H, W, seed=seed)
+        hb = {"color_u8": torch.stack([(i[("color", f, 0)].permute(0, 2, 3, 1) * 255).round().clamp(0, 255).to(torch.uint8)
+                                       for f in frames], 0).contiguous()}
+        hb.update({k: v for k, v in i.items() if not (isinstance(k, tuple) and k[0] == "color")})
+        hb.update({k: v for k, v in o.items() if k[0] in ("disp", "cam_T_cam")})
+        batches.append(hostio.PinnedBatch(hb))
+    d, arena = batches[0].upload(dev)
+    inp = {k: v for k, v in d.items() if not (isinstance(k, tuple) and k[0] in ("disp", "cam_T_cam"))}
+    out = {k: v.requires_grad_(True) for k, v in d.items() if isinstance(k, tuple) and k[0] in ("disp", "cam_T_cam")}
+    runner = trainer_hooks.GraphedLoss(ns)
+    slot = runner.capture(inp, out)
+    for hb in batches:
+        hb.upload_into(arena)
+        for v in out.values():
+            v.grad = None
+        losses = slot.replay()
+        losses["loss"].backward()
+        got = {k: v.detach().clone() for k, v in losses.items()}
+        got_g = {k: v.grad.clone() for k, v in out.items()}
+        got_am = {s: out[("argmin", s)].clone() for s in opt.scales} if ("argmin", 0) in out else None
+        # eager reference on copies of the same device tensors
+        d2, _ = hb.upload(dev)
+        inp2 = {k: v for k, v in d2.items() if not (isinstance(k, tuple) and k[0] in ("disp", "cam_T_cam"))}
+        out2 = {k: v.requires_grad_(True) for k, v in d2.items() if isinstance(k, tuple) and k[0] in ("disp", "cam_T_cam")}
+        trainer_hooks.ingest_colors(inp2, frames, 4, device=dev)
+        o2 = SimpleNamespace(**vars(opt)); o2.pml_noise = "philox"
+        ns2 = SimpleNamespace(opt=o2, device=dev, num_scales=4)
+        trainer_hooks.generate_images_pred(ns2, inp2, out2)
+        want = trainer_hooks.compute_losses(ns2, inp2, out2)
+        want["loss"].backward()
+        for k in want:
+            assert common.rel_err(got[k].cpu(), want[k].detach().cpu()) < 2e-6, k     # another Philox stream on near-ties only
+        for k in out2:
+            assert common.rel_err(got_g[k].cpu(), out2[k].grad.cpu()) < 1e-3, k
+        if got_am is not None:
+            for s in opt.scales:
+                assert (got_am[s] != out2[("argmin", s)]).float().mean().item() < 1e-3
+
+
 def test_tensors_on_a_non_current_device(cuda_lib):
     """The reference trainer keeps its tensors on cuda:1 / cuda:3 without ever calling set_device
     (trainer.py:44,67): every libpml launch must follow its tensors' device, not the current one."""
