@@ -142,12 +142,13 @@ def test_graphed_loss_matches_the_eager_dropins(cuda_lib):
     slot = runner.capture(inp, out)
     for hb in batches:
         hb.upload_into(arena)
-        for v in out.values():
-            v.grad = None
+        for k, v in out.items():
+            if k[0] in ("disp", "cam_T_cam"):
+                v.grad = None
         losses = slot.replay()
         losses["loss"].backward()
         got = {k: v.detach().clone() for k, v in losses.items()}
-        got_g = {k: v.grad.clone() for k, v in out.items()}
+        got_g = {k: v.grad.clone() for k, v in out.items() if k[0] in ("disp", "cam_T_cam")}
         got_am = {s: out[("argmin", s)].clone() for s in opt.scales} if ("argmin", 0) in out else None
         # eager reference on copies of the same device tensors
         d2, _ = hb.upload(dev)
