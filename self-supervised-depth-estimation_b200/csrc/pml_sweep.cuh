@@ -217,6 +217,13 @@ sweep_kernel(const PhotoParams p) {
         }
         const float fxc = (float)rx;
         rc0 = ikb[0] * fxc; rc1 = ikb[4] * fxc; rc2 = ikb[8] * fxc;
+        // The adjoint block reads ring slots before the first rows have been written (and for lanes / rows that own
+        // nothing) and masks du / dv, not the factors it multiplies them with: whatever shared memory held before
+        // this CTA (e.g. the byte patterns of the pyramid kernel = NaN as floats) must not reach 0 * garbage
+        if (GRAD) {
+#pragma unroll
+            for (int k = 0; k < kSweepRingSlots * kSweepRingQ; ++k) sRing[k * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         __syncwarp();
     }
 

@@ -17,6 +17,7 @@
 #include <functional>
 #include <memory>
 #include <thread>
+#include <algorithm>
 #include <vector>
 
 #define PML_HOST_EMU 1
@@ -139,6 +140,9 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& body_in) {
             blk.bid = {(unsigned)(i % grid.x), (unsigned)((i / grid.x) % grid.y), (unsigned)(i / ((unsigned long long)grid.x * grid.y))};
             blk.all = Group{nt, 0, 0};
             for (unsigned w = 0; w < nwarps; ++w) blk.warps[w] = Group{std::min(32u, nt - w * 32), 0, 0};
+            // dynamic shared memory starts out as whatever the previous CTA on that SM left behind: poison it with
+            // the NaN bit pattern so that a kernel relying on its initial contents fails on the CPU too
+            std::fill(blk.smem.begin(), blk.smem.end(), (unsigned char)0xFF);
             run_block(blk);
         }
     };
