@@ -363,13 +363,17 @@ def run_ours(args, rank, world, dev):
         o2.pml_sources, o2.pml_variant, o2.pml_emit_depth = srcs, "trainer", "scale0"
         ns = SimpleNamespace(opt=o2, device=dev, num_scales=len(opt.scales))
         frames = [0] + list(srcs)
-        host = []
+        host, net = [], []
         for (i, o) in sets:
             hb = {"color_u8": torch.stack([(i[("color", f, 0)].permute(0, 2, 3, 1) * 255.0).round().clamp(0, 255)
                                            .to(torch.uint8) for f in frames], 0).contiguous()}
             hb.update({k: v for k, v in i.items() if not (isinstance(k, tuple) and k[0] == "color")})
-            hb.update({k: v for k, v in o.items() if k[0] in ("disp", "cam_T_cam")})
-            host.append(hostio.PinnedBatch(hb))
+            host.append(hostio.PinnedBatch(hb))          # what the DataLoader delivers: frames + intrinsics
+            # what the networks deliver (disparities, poses) never crosses PCIe in training: device-resident, a
+            # different set every step, copied into the slot like a network would write its outputs
+            net.append({k: v.to(dev) for k, v in o.items() if k[0] in ("disp", "cam_T_cam")})
+        diff_keys = sorted(net[0].keys(), key=str)
+        d2d = sum(v.numel() * v.element_size() for v in net[0].values())
         runner = trainer_hooks.GraphedLoss(ns)
         copy_stream = torch.cuda.Stream(device=dev)
         main_stream = torch.cuda.current_stream(dev)
@@ -377,8 +381,8 @@ def run_ours(args, rank, world, dev):
         for s in range(2):
             d, arena = host[0].upload(dev)
             torch.cuda.synchronize()
-            inp = {k: v for k, v in d.items() if not (isinstance(k, tuple) and k[0] in ("disp", "cam_T_cam"))}
-            out = {k: v.requires_grad_(True) for k, v in d.items() if isinstance(k, tuple) and k[0] in ("disp", "cam_T_cam")}
+            inp = dict(d)
+            out = {k: net[0][k].clone().requires_grad_(True) for k in diff_keys}
             slot = runner.capture(inp, out)
             done = torch.cuda.Event()
             done.record(main_stream)
@@ -393,11 +397,13 @@ def run_ours(args, rank, world, dev):
                 ev.record(copy_stream)
             return ev
 
-        def compute(s, ev):
+        def compute(s, ev, i):
             slot, arena, out, done = slots[s]
             main_stream.wait_event(ev)
-            for v in out.values():
-                v.grad = None
+            for k in diff_keys:
+                out[k].grad = None
+            with torch.no_grad():     # this step's network outputs land in the slot (one multi-tensor copy)
+                torch._foreach_copy_([out[k] for k in diff_keys], [net[i % len(net)][k] for k in diff_keys])
             losses = slot.replay()
             losses["loss"].backward()
             done.record(main_stream)
@@ -410,7 +416,7 @@ def run_ours(args, rank, world, dev):
                 cur = nxt
                 if i + 1 < n:
                     nxt = upload(host[(i + 1) % len(host)], (i + 1) % 2)
-                last = compute(i % 2, cur).item()   # D2H read of the step's result
+                last = compute(i % 2, cur, i).item()   # D2H read of the step's result
             return last
 
         Ke = max(3, min(K, 100))
@@ -424,8 +430,9 @@ def run_ours(args, rank, world, dev):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return {"value": round(world * n_pix * Ke / t.item() / 1e6, 2), "unit": UNIT, "h2d_bytes_per_step": int(host[0].nbytes),
-                "d2h_bytes_per_step": 4, "steps": Ke, "ms_per_step": round(t.item() / Ke * 1e3, 4), "copies_declared": True,
-                "host_input": "u8",
+                "d2h_bytes_per_step": 4, "d2d_bytes_per_step": int(d2d), "steps": Ke, "ms_per_step": round(t.item() / Ke * 1e3, 4),
+                "copies_declared": True, "host_input": "uint8 scale-0 frames + intrinsics (the DataLoader's batch); disparities and poses "
+                "(network outputs) device-resident, a different set copied into the slot every step",
                 "api": "trainer_hooks.GraphedLoss (opt-in CUDA-graph mode of the drop-in pair generate_images_pred + compute_losses, "
                        "uint8 ingest inside the graph): per step one H2D copy of the pinned host arena (hostio.PinnedBatch) into a "
                        "static slot on a copy stream, slot.replay(), loss.backward(), loss.item(); two slots, upload of step i+1 "

@@ -14,7 +14,6 @@ for name in ("trainer_default", "trainer_predmask", "trainer_wide", "gru_seq3", 
     variant, opt, inputs, outputs, r32, r64, seed = common.load_golden(name)
     got = common.run_product(opt, inputs, outputs, variant, device="cpu", noise_seed=seed)
     print(name, "ok", float(got["loss"]))
-os.environ["PML_KERNEL"] = "sweep"
 for sources, (B, H, W) in (((-1, 1, -2, 2, "s"), (1, 32, 64)), ((-1, 1, -2, 2, -3, 3, -4, 4), (1, 32, 64)), ((-1, 1), (3, 40, 104)), ((1,), (2, 24, 40))):
     opt = synthetic.make_options(H, W, batch_size=B, scales=[0, 1, 2] if H % 8 else [0, 1, 2, 3])
     inputs, outputs = synthetic.make_batch(B, H, W, sources=sources, seed=6, scales=opt.scales)
@@ -26,6 +25,24 @@ for (N, H, W, n) in ((2, 96, 160, 4), (1, 32, 64, 4), (1, 8, 16, 4), (1, 40, 72,
     fr = torch.from_numpy(rng.integers(0, 256, (N, H, W, 3), dtype=np.uint8))
     out = Fn.color_pyramid(fr, n)
     print("pyramid", (N, H, W, n), "ok", float(out[-1].mean()))
+# disparity heads: forward / backward on sizes off the 30-column strips and 16-row chunks, channel split over warps
+for (B, C, h, w) in ((2, 16, 37, 95), (1, 128, 6, 5), (1, 64, 17, 31), (3, 32, 16, 30)):
+    x = torch.randn(B, C, h, w, requires_grad=True)
+    wt, bs = (torch.randn(1, C, 3, 3) * 0.1).requires_grad_(True), torch.zeros(1, requires_grad=True)
+    d = Fn.disp_head(x, wt, bs)
+    d.backward(torch.randn_like(d))
+    print("disp head", (B, C, h, w), "ok", float(d.mean()))
+# selection masks: pixel counts off the 16-pixel vector path
+for n in ((2, 3, 5, 7), (4, 1, 8, 16), (1, 2, 33, 65)):
+    am = torch.randint(0, 4, n, dtype=torch.uint8)
+    m = Fn.selection_masks(am, 2)
+    assert torch.equal(m, (am > 1).float())
+print("selection masks ok")
+# cross-check kernel (CTA strips) on a multi-strip shape
+opt = synthetic.make_options(40, 104, batch_size=2, scales=[0, 1, 2])
+inputs, outputs = synthetic.make_batch(2, 40, 104, seed=6, scales=opt.scales)
+got = common.run_product(opt, inputs, outputs, "trainer", device="cpu", noise_seed=3, extra_opt=dict(pml_kernel="cta"))
+print("cta kernel ok", float(got["loss"]))
 import layer_checks
 layer_checks.run("cpu"); layer_checks.depth_metrics("cpu")
 print("layers ok")
