@@ -214,10 +214,14 @@ int pml_pyramid_u8(const uint8_t* frames, int32_t N, int32_t H, int32_t W, int32
 /* ---- monitoring metrics: Trainer.compute_depth_losses (trainer.py:624-652) over
  * layers.compute_depth_errors (layers.py:251-269).  prepare resizes depth [B,1,H,W] to the ground
  * truth's [B,1,Hg,Wg] (bilinear, align_corners=False), clamps, applies mask = gt>0 & crop and writes
- * dense pred/gt arrays (+inf where masked) plus the valid count; the caller takes the two medians
- * (element (count-1)/2 of each sorted array == torch.median) and passes their ratio to reduce,
- * which returns abs_rel, sq_rel, rmse, rmse_log, a1, a2, a3. ---- */
+ * dense pred/gt arrays (+inf where masked) plus the valid count; median_ratio finds the two medians
+ * (element (count-1)/2 of each sorted array == torch.median) and reduce, given their ratio,
+ * returns abs_rel, sq_rel, rmse, rmse_log, a1, a2, a3. ---- */
 size_t pml_depth_metrics_workspace_bytes(void);
+/* ratio[0] = median(gt) / median(pred) over the valid entries (trainer.py:645), torch.median's lower-middle element,
+ * found by radix selection on the device (no sort).  The workspace is the one of pml_depth_metrics_workspace_bytes. */
+int pml_depth_metrics_median_ratio(const float* pred, const float* gt, int64_t n, const int32_t* count, float* ratio,
+                                   void* workspace, size_t workspace_bytes, pml_stream_t);
 int pml_depth_metrics_prepare(const float* depth, const float* depth_gt, float* pred_out, float* gt_out, int32_t* count,
                               int32_t B, int32_t H, int32_t W, int32_t Hg, int32_t Wg, int32_t crop_y0, int32_t crop_y1,
                               int32_t crop_x0, int32_t crop_x1, float min_depth, float max_depth, pml_stream_t);

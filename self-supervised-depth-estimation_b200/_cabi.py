@@ -91,6 +91,7 @@ _SIGNATURES = {
     "pml_depth_metrics_workspace_bytes": (c_size_t, []),
     "pml_depth_metrics_prepare": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int32] * 9 +
                                   [c_float, c_float, c_void_p]),
+    "pml_depth_metrics_median_ratio": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "pml_depth_metrics_reduce": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_float, c_float, c_void_p,
                                          c_void_p, c_size_t, c_void_p]),
 }

@@ -68,6 +68,84 @@ depth_metrics_prepare_kernel(const MetricsPrepParams q) {
 
 constexpr int kMetricsBlocks = 296;   // 2 per SM
 
+// ---- medians (trainer.py:645: torch.median(gt) / torch.median(pred) over the valid pixels) by radix selection:
+// torch.median returns the lower middle element, i.e. element k = (n_valid - 1) / 2 of the sorted values; the arrays
+// hold non-negative floats (+inf where masked), whose bit patterns order like the values.  Three histogram passes
+// over 11 + 11 + 10 key bits narrow the k-th element down exactly; no sort, no host synchronisation.
+constexpr int kSelBins = 2048;
+constexpr int kSelBlocks = 296;
+struct SelectParams {
+    const float* a[2];      // gt, pred (dense, +inf where masked)
+    long long n;
+    const int* count;       // n_valid
+    unsigned* hist;         // [2][kSelBins]
+    unsigned* state;        // [2][2]: key prefix found so far, rank k inside it
+    float* ratio;           // out: median(a[0]) / median(a[1])
+    int pass;               // 0, 1, 2
+};
+__device__ __forceinline__ int sel_shift(int pass) { return pass == 0 ? 21 : (pass == 1 ? 10 : 0); }
+__device__ __forceinline__ int sel_bits(int pass) { return pass == 2 ? 10 : 11; }
+
+__global__ void __launch_bounds__(256)
+select_init_kernel(const SelectParams q) {
+    for (int i = threadIdx.x; i < 2 * kSelBins; i += 256) q.hist[i] = 0u;
+    if (threadIdx.x < 2) {
+        const int c = *q.count;
+        q.state[threadIdx.x * 2 + 0] = 0u;
+        q.state[threadIdx.x * 2 + 1] = (unsigned)(c > 0 ? (c - 1) / 2 : 0);
+    }
+}
+
+// grid = (kSelBlocks, 2)
+__global__ void __launch_bounds__(256)
+select_hist_kernel(const SelectParams q) {
+    __shared__ unsigned s_h[kSelBins];
+    const int arr = blockIdx.y;
+    for (int i = threadIdx.x; i < kSelBins; i += 256) s_h[i] = 0u;
+    __syncthreads();
+    const int shift = sel_shift(q.pass), bits = sel_bits(q.pass);
+    const unsigned prefix = q.state[arr * 2];
+    const float* a = q.a[arr];
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < q.n; i += (long long)gridDim.x * 256) {
+        const unsigned key = __float_as_uint(__ldg(a + i));
+        // pass 0 looks at every element; later passes only at those inside the prefix found so far
+        if (q.pass == 0 || (key >> (shift + bits)) == prefix) atomicAdd(&s_h[(key >> shift) & ((1u << bits) - 1u)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kSelBins; i += 256)
+        if (s_h[i]) atomicAdd(q.hist + arr * kSelBins + i, s_h[i]);
+}
+
+// grid = 2 (one block per array): locate the bin that holds rank k, extend the prefix, clear the histogram
+__global__ void __launch_bounds__(256)
+select_scan_kernel(const SelectParams q) {
+    __shared__ unsigned s_bin, s_before;
+    const int arr = blockIdx.x;
+    unsigned* h = q.hist + arr * kSelBins;
+    const int nb = 1 << sel_bits(q.pass);
+    if (threadIdx.x == 0) {
+        const unsigned k = q.state[arr * 2 + 1];
+        unsigned cum = 0, bin = (unsigned)(nb - 1), before = 0;
+        for (int i = 0; i < nb; ++i) {
+            const unsigned c = h[i];
+            if (cum + c > k) { bin = (unsigned)i; before = cum; break; }
+            cum += c;
+            before = cum;
+        }
+        s_bin = bin; s_before = before;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kSelBins; i += 256) h[i] = 0u;
+    if (threadIdx.x == 0) {
+        q.state[arr * 2 + 0] = (q.state[arr * 2 + 0] << sel_bits(q.pass)) | s_bin;
+        q.state[arr * 2 + 1] -= s_before;
+    }
+}
+
+__global__ void select_ratio_kernel(const SelectParams q) {
+    if (threadIdx.x == 0) q.ratio[0] = __uint_as_float(q.state[0]) / __uint_as_float(q.state[2]);   // trainer.py:645
+}
+
 // part: [kMetricsBlocks][8]; sums of abs_rel, sq_rel, sq err, sq log err, a1, a2, a3
 __global__ void __launch_bounds__(256)
 depth_metrics_reduce_kernel(const float* __restrict__ pred, const float* __restrict__ gt, long long n,

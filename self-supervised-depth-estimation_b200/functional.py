@@ -726,9 +726,8 @@ def depth_metrics(depth_pred: torch.Tensor, depth_gt: torch.Tensor, crop=GARG_CR
     resolution), depth_gt [B,1,Hg,Wg] (0 = no measurement) -> 7 floats on the device in the order of
     ``depth_metric_names``: abs_rel, sq_rel, rmse, rmse_log, a1, a2, a3.
 
-    Resize + clamp + mask + crop run in one kernel, median scaling + the seven error sums in a
-    second one; the two medians in between are taken with torch.sort on the device (a library
-    selection, like the reference's torch.median).  No host synchronisation."""
+    Resize + clamp + mask + crop run in one kernel, the two medians are found by radix selection (three
+    histogram passes, no sort), median scaling + the seven error sums in a last one.  No host synchronisation."""
     lib = get_library()
     depth_pred = _check(depth_pred.detach(), "depth_pred", lib)
     depth_gt = _check(depth_gt, "depth_gt", lib)
@@ -747,12 +746,13 @@ def depth_metrics(depth_pred: torch.Tensor, depth_gt: torch.Tensor, crop=GARG_CR
     lib.check(lib.pml_depth_metrics_prepare(_ptr(depth_pred), _ptr(depth_gt), _ptr(pred), _ptr(gt), _ptr(count),
                                             B, H, W, Hg, Wg, cy0, cy1, cx0, cx1, float(min_depth), float(max_depth), st),
               "pml_depth_metrics_prepare")
-    # torch.median == lower middle element == sorted[(n_valid - 1) // 2]; masked entries are +inf
-    k = ((count.to(torch.int64) - 1).clamp_(min=0)) // 2
-    ratio = (torch.sort(gt).values[k] / torch.sort(pred).values[k]).to(torch.float32).contiguous()   # trainer.py:645
+    # torch.median == lower middle element == sorted[(n_valid - 1) // 2]; masked entries are +inf: radix selection on the device
+    ratio = torch.empty(1, device=dev, dtype=torch.float32)
     out = torch.empty(7, device=dev, dtype=torch.float32)
     nb = lib.pml_depth_metrics_workspace_bytes()
     ws = torch.empty(nb, device=dev, dtype=torch.uint8)
+    lib.check(lib.pml_depth_metrics_median_ratio(_ptr(pred), _ptr(gt), n, _ptr(count), _ptr(ratio), _ptr(ws), nb, st),
+              "pml_depth_metrics_median_ratio")                                                          # trainer.py:645
     lib.check(lib.pml_depth_metrics_reduce(_ptr(pred), _ptr(gt), n, _ptr(ratio), _ptr(count), float(min_depth),
                                            float(max_depth), _ptr(out), _ptr(ws), nb, st), "pml_depth_metrics_reduce")
     return out
