@@ -169,6 +169,45 @@ def test_graphed_loss_matches_the_eager_dropins(cuda_lib):
                 assert (got_am[s] != out2[("argmin", s)]).float().mean().item() < 1e-3
 
 
+def test_graphed_loss_dropin_call_with_network_outputs(cuda_lib):
+    """GraphedLoss.__call__: this step's tensors live at new addresses (a DataLoader batch, network outputs with an
+    autograd history); they are copied into slot 0, the graph is replayed and the gradients flow back into the
+    'network' parameters like through the eager drop-ins."""
+    from types import SimpleNamespace
+    from ssde_b200 import trainer_hooks
+    dev = torch.device("cuda")
+    B, H, W = 2, 64, 160
+    opt = synthetic.make_options(H, W, batch_size=B)
+    opt.pml_sources, opt.pml_variant, opt.pml_emit_depth, opt.pml_noise = [-1, 1], "trainer", "scale0", "philox"
+    ns = SimpleNamespace(opt=opt, device=dev, num_scales=4)
+    runner = trainer_hooks.GraphedLoss(ns)
+    for seed in (4, 5, 6):
+        i, o = synthetic.make_batch(B, H, W, seed=seed)
+        inp = {k: v.to(dev) for k, v in i.items()}
+        res = {}
+        for mode in ("graph", "eager"):
+            # a stand-in network: disparity = sigmoid(logit parameter), pose = parameter
+            logits = {s: torch.logit(o[("disp", s)].to(dev).clamp(1e-3, 1 - 1e-3)).requires_grad_(True) for s in opt.scales}
+            poses = {f: o[("cam_T_cam", 0, f)].to(dev).clone().requires_grad_(True) for f in (-1, 1)}
+            out = {("disp", s): torch.sigmoid(logits[s]) for s in opt.scales}
+            out.update({("cam_T_cam", 0, f): poses[f] * 1.0 for f in (-1, 1)})
+            if mode == "graph":
+                losses = runner(dict(inp), out)
+            else:
+                trainer_hooks.generate_images_pred(ns, dict(inp), out)
+                losses = trainer_hooks.compute_losses(ns, dict(inp), out)
+            losses["loss"].backward()
+            res[mode] = (losses["loss"].detach().clone(), {s: logits[s].grad.clone() for s in opt.scales},
+                         {f: poses[f].grad.clone() for f in (-1, 1)}, out[("depth", 0, 0)].detach().clone())
+        g, e = res["graph"], res["eager"]
+        assert common.rel_err(g[0].cpu(), e[0].cpu()) < 2e-6
+        for s in opt.scales:
+            assert parity.l2_err(g[1][s].cpu(), e[1][s].cpu()) < 2e-2, s      # different Philox streams on near-ties
+        for f in (-1, 1):
+            assert parity.l2_err(g[2][f].cpu(), e[2][f].cpu()) < 2e-2, f
+        assert common.rel_err(g[3].cpu(), e[3].cpu()) < 1e-6
+
+
 def test_tensors_on_a_non_current_device(cuda_lib):
     """The reference trainer keeps its tensors on cuda:1 / cuda:3 without ever calling set_device
     (trainer.py:44,67): every libpml launch must follow its tensors' device, not the current one."""
