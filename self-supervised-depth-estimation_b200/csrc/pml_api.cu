@@ -278,7 +278,7 @@ int launch_sweep(const PhotoParams& pp, cudaStream_t st) {
     for (int i = 0; i < pp.n_pass; ++i) emit = emit || pp.pass[i].depth != nullptr || pp.pass[i].warped != nullptr;
     const dim3 blk(kSweepWarps * 32);
     if (pp.mode == 2) emit = false;   // the adjoint sweeps of earlier pairs never write by-products
-    bool common = !emit && pp.pair_n == 2 && (pp.mode != 0 || pp.S == 2) &&
+    bool common = !emit && (pp.mode != 0 ? pp.pair_n >= 1 : (pp.pair_n == 2 && pp.S == 2)) &&
                   !(pp.flags & (PML_FLAG_NO_AUTOMASK | PML_FLAG_AVG_REPROJ));
     for (int i = 0; i < pp.n_pass; ++i) common = common && pp.pass[i].noise == nullptr && pp.pass[i].fw == nullptr;
     if (pp.mode == 0) {

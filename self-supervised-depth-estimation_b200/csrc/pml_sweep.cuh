@@ -176,7 +176,7 @@ sweep_kernel(const PhotoParams p) {
     const int n_sel = COMMON ? (MODE == 0 ? 2 : S) : (automask ? (avg ? 1 : S) : 0);   // identity candidates of the selection
     const int n_id = (mode == 0) ? n_sel : 0;             // ... evaluated by this launch
     const int fa = (COMMON && MODE == 0) ? 0 : p.f_base;  // frames in the two halves of every pair
-    const bool two = COMMON ? true : p.pair_n > 1;
+    const bool two = (COMMON && MODE == 0) ? true : p.pair_n > 1;   // modes 1-3: the last pair of an odd frame count has one frame
     const int fb = two ? fa + 1 : fa;                     // one frame: it is aliased into the second half
 
     // ---- per-warp shared memory ----------------------------------------------------------------
@@ -598,25 +598,6 @@ sweep_kernel(const PhotoParams p) {
                 const int pix = py * W + cx;
                 float best = 3.0e38f;
                 int best_i = 0;
-                // identity candidates + tie-break noise (trainer.py:592-597), any number of them
-                for (int i = 0; i < n_sel; i += 2) {
-                    float n0 = 0.f, n1 = 0.f;
-                    const int o = (b * n_sel + i) * plane + pix;
-                    if (nz_g != nullptr) {
-                        n0 = __ldg(at(nz_g, o));
-                        if (i + 1 < n_sel) n1 = __ldg(at(nz_g, o + plane));
-                    } else {
-                        const unsigned long long sd = p.seed_dev ? (p.seed ^ __ldg(p.seed_dev)) : p.seed;
-                        philox2_normal2((uint32_t)sd ^ ((uint32_t)(sd >> 32) * 0x9E3779B9u), (uint32_t)(bp + pix),
-                                        (uint32_t)pass_i + 0x10000u * (uint32_t)(i >> 1), n0, n1);
-                    }
-                    const float c0 = fmaf(n0, kTieNoise, __ldg(at(id_g, o)));
-                    if (c0 < best) { best = c0; best_i = i; }
-                    if (i + 1 < n_sel) {
-                        const float c1 = fmaf(n1, kTieNoise, __ldg(at(id_g, o + plane)));
-                        if (c1 < best) { best = c1; best_i = i + 1; }
-                    }
-                }
                 // reprojection losses of the pairs swept before (mode 1), in frame order, then this pair;
                 // the predictive mask weighs every frame (trainer.py:579)
                 const float* rq = p.rp + ((size_t)(pass_i * S) * p.B + b) * plane + pix;   // frame stride: B * plane
@@ -631,14 +612,45 @@ sweep_kernel(const PhotoParams p) {
                 const float2 m = (mq != nullptr) ? f2(__ldg(at(mq, fa * plane)), two ? __ldg(at(mq, fb * plane)) : 0.f) : splat(1.f);
                 const float2 rw = mul2(rp, m);
                 if (avg) {
-                    const float mean = (rsum + rw.x + (two ? rw.y : 0.f)) / (float)S;     // trainer.py:585-586
-                    if (mean < best) { best = mean; best_i = n_sel; }
-                    wgt = (best_i == n_sel) ? f2(1.0f / (float)S, two ? 1.0f / (float)S : 0.f) : splat(0.f);
+                    best = (rsum + rw.x + (two ? rw.y : 0.f)) / (float)S;     // trainer.py:585-586
+                    best_i = n_sel;
                 } else {
                     if (rw.x < best) { best = rw.x; best_i = n_sel + fa; }
                     if (two && rw.y < best) { best = rw.y; best_i = n_sel + fb; }
-                    wgt = f2(best_i == n_sel + fa ? 1.f : 0.f, (two && best_i == n_sel + fb) ? 1.f : 0.f);
                 }
+                // identity candidates + tie-break noise (trainer.py:592-597), any number of them.  They precede the
+                // reprojection candidates in the reference's order (torch.min returns the first minimum), hence `<=` below.
+                // In-kernel noise is bounded (|n| <= 6.66, see above): an identity candidate further than 1.4e-4 above
+                // the best reprojection candidate cannot win whatever the noise, and the generator is skipped.
+                if (n_sel > 0) {
+                    float m_id = 3.0e38f;
+                    for (int i = 0; i < n_sel; ++i) m_id = fminf(m_id, __ldg(at(id_g, (b * n_sel + i) * plane + pix)));
+                    if (nz_g != nullptr || m_id - best < 1.4e-4f) {
+                        float ib = 3.0e38f;
+                        int ib_i = 0;
+                        for (int i = 0; i < n_sel; i += 2) {
+                            float n0 = 0.f, n1 = 0.f;
+                            const int o = (b * n_sel + i) * plane + pix;
+                            if (nz_g != nullptr) {
+                                n0 = __ldg(at(nz_g, o));
+                                if (i + 1 < n_sel) n1 = __ldg(at(nz_g, o + plane));
+                            } else {
+                                const unsigned long long sd = p.seed_dev ? (p.seed ^ __ldg(p.seed_dev)) : p.seed;
+                                philox2_normal2((uint32_t)sd ^ ((uint32_t)(sd >> 32) * 0x9E3779B9u), (uint32_t)(bp + pix),
+                                                (uint32_t)pass_i + 0x10000u * (uint32_t)(i >> 1), n0, n1);
+                            }
+                            const float c0 = fmaf(n0, kTieNoise, __ldg(at(id_g, o)));
+                            if (c0 < ib) { ib = c0; ib_i = i; }
+                            if (i + 1 < n_sel) {
+                                const float c1 = fmaf(n1, kTieNoise, __ldg(at(id_g, o + plane)));
+                                if (c1 < ib) { ib = c1; ib_i = i + 1; }
+                            }
+                        }
+                        if (ib <= best) { best = ib; best_i = ib_i; }
+                    }
+                }
+                if (avg) wgt = (best_i == n_sel) ? f2(1.0f / (float)S, two ? 1.0f / (float)S : 0.f) : splat(0.f);
+                else wgt = f2(best_i == n_sel + fa ? 1.f : 0.f, (two && best_i == n_sel + fb) ? 1.f : 0.f);
                 if (col_owned && py >= y0 && py < y1) {
                     loss_acc += best;
                     if (ps.argmin != nullptr) ps.argmin[bp + pix] = (uint8_t)best_i;
