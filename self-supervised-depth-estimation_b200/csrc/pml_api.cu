@@ -34,7 +34,7 @@ struct Plan {
     int n_id;
     int smooth_blocks[PML_MAX_PASSES], smooth_off[PML_MAX_PASSES], smooth_total;
     int max_chunks;
-    size_t off_identity, off_part, off_mean, off_meanpart, off_imagepart, off_smooth, off_rp, off_argmin, total;
+    size_t off_identity, off_part, off_mean, off_meanpart, off_imagepart, off_smooth, off_rp, off_argmin, off_presel, total;
 };
 
 inline void pml_event_record(void* ev, cudaStream_t st) {
@@ -210,7 +210,7 @@ Plan make_plan(const pml_problem* p, bool grad) {
         }
         return best_th;
     };
-    pl.TH_fwd = pl.sweep ? sweep_rows(common_fwd ? 16 : 12) : chunk_rows(kNumSM * 6);
+    pl.TH_fwd = pl.sweep ? sweep_rows(kSweepFwdCtas) : chunk_rows(kNumSM * 6);
     pl.TH = (pl.sweep && !grad) ? pl.TH_fwd : (pl.sweep ? sweep_rows(8) : chunk_rows(kNumSM * 6));
     pl.n_chunks = (p->H + pl.TH - 1) / pl.TH;
     pl.n_chunks_fwd = (p->H + pl.TH_fwd - 1) / pl.TH_fwd;
@@ -240,11 +240,13 @@ Plan make_plan(const pml_problem* p, bool grad) {
     pl.off_meanpart = off; off = align16(off + (size_t)p->n_pass * p->B * pl.max_chunks * sizeof(float));
     pl.off_imagepart = off; off = align16(off + (size_t)p->n_pass * p->B * 4 * sizeof(float));
     pl.off_smooth = off;   off = align16(off + (size_t)pl.smooth_total * 3 * sizeof(float));
-    pl.off_rp = pl.off_argmin = off;
+    pl.off_rp = pl.off_argmin = pl.off_presel = off;
     pl.two_sweeps = pl.sweep && (p->S > 2 || p->pass[0].frame_weight != nullptr);
     if (pl.two_sweeps) {   // pair-by-pair sweep: reprojection losses of all frames + a selection map
         off = align16(off + (size_t)p->n_pass * p->S * p->B * p->H * p->W * sizeof(float));
         pl.off_argmin = off;
+        off = align16(off + (size_t)p->n_pass * p->B * p->H * p->W);
+        pl.off_presel = off;
         off = align16(off + (size_t)p->n_pass * p->B * p->H * p->W);
     }
     pl.total = off;
@@ -269,18 +271,27 @@ int launch_photo(const PhotoParams& pp, int n_cta, int NT, int low_cells, cudaSt
     return PML_OK;
 }
 
+// the instantiation without run-time flag tests: default flags, in-kernel noise, no by-product stores
+bool sweep_common(const PhotoParams& pp) {
+    bool emit = false;   // by-products requested by any pass (never in sweep mode 2)
+    for (int i = 0; i < pp.n_pass; ++i) emit = emit || pp.pass[i].depth != nullptr || pp.pass[i].warped != nullptr;
+    if (pp.mode == 2) emit = false;
+    bool common = !emit && (pp.mode != 0 ? pp.pair_n >= 1 : (pp.pair_n == 2 && pp.S == 2)) &&
+                  !(pp.flags & (PML_FLAG_NO_AUTOMASK | PML_FLAG_AVG_REPROJ));
+    for (int i = 0; i < pp.n_pass; ++i) common = common && pp.pass[i].noise == nullptr && pp.pass[i].fw == nullptr;
+    return common;
+}
+
 template <bool GRAD, bool SSIM>
 int launch_sweep(const PhotoParams& pp, cudaStream_t st) {
-    const size_t smem = sweep_smem_bytes() + (size_t)knobs().smem_pad;   // < 48 KB: no opt-in needed
+    const size_t smem = sweep_smem_bytes(GRAD && pp.mode != 1) + (size_t)(GRAD ? knobs().smem_pad : 0);   // < 48 KB: no opt-in needed
     if (pp.B > 65535) return PML_ERR_UNSUPPORTED;
     const dim3 grid(pp.n_chunks * pp.n_strips, pp.B, pp.n_pass);
     bool emit = false;   // by-products requested by any pass (never in sweep mode 2)
     for (int i = 0; i < pp.n_pass; ++i) emit = emit || pp.pass[i].depth != nullptr || pp.pass[i].warped != nullptr;
     const dim3 blk(kSweepWarps * 32);
     if (pp.mode == 2) emit = false;   // the adjoint sweeps of earlier pairs never write by-products
-    bool common = !emit && (pp.mode != 0 ? pp.pair_n >= 1 : (pp.pair_n == 2 && pp.S == 2)) &&
-                  !(pp.flags & (PML_FLAG_NO_AUTOMASK | PML_FLAG_AVG_REPROJ));
-    for (int i = 0; i < pp.n_pass; ++i) common = common && pp.pass[i].noise == nullptr && pp.pass[i].fw == nullptr;
+    const bool common = sweep_common(pp);
     if (pp.mode == 0) {
         if (common)    PML_LAUNCH((sweep_kernel<GRAD, SSIM, 0, false, true>), grid, blk, smem, st, pp);
         else if (emit) PML_LAUNCH((sweep_kernel<GRAD, SSIM, 0, true>), grid, blk, smem, st, pp);
@@ -420,7 +431,7 @@ int run_loss(const pml_problem* p, void* ws, size_t ws_bytes, cudaStream_t st, b
     }
     pp.TW = pl.TW; pp.TH = pl.TH; pp.n_strips = pl.n_strips; pp.n_chunks = pl.n_chunks;
     pp.n_items = pl.n_cta; pp.S = p->S;
-    pp.mode = 0; pp.f_base = 0; pp.pair_n = p->S > 1 ? 2 : 1; pp.rp = nullptr;
+    pp.mode = 0; pp.f_base = 0; pp.pair_n = p->S > 1 ? 2 : 1; pp.rp = nullptr; pp.presel = nullptr;
     pp.cta_per_pass = pl.cta_per_pass; pp.part = part; pp.part_stride = pl.part_stride;
     pp.inv_n = (float)(1.0 / ((double)p->B * p->H * p->W));
     pp.n_seg = sp.n_seg; pp.seg_size = sp.seg_size;
@@ -449,6 +460,9 @@ int run_loss(const pml_problem* p, void* ws, size_t ws_bytes, cudaStream_t st, b
         pp.TH = pl.TH; pp.n_chunks = pl.n_chunks;
         if (rc == PML_OK) {
             pp.mode = 3; pp.f_base = last_fa; pp.pair_n = (last_fa + 1 < p->S) ? 2 : 1;
+            pp.presel = reinterpret_cast<uint8_t*>(base + pl.off_presel);
+            if (sweep_common(pp))   // candidates ahead of the last pair -> one value + one index per pixel
+                PML_LAUNCH(select_prepass_kernel, dim3((p->H * p->W + 255) / 256, p->B, p->n_pass), dim3(256), 0, st, pp);
             if (grad) rc = ssim ? launch_sweep<true, true>(pp, st) : launch_sweep<true, false>(pp, st);
             else      rc = ssim ? launch_sweep<false, true>(pp, st) : launch_sweep<false, false>(pp, st);
         }

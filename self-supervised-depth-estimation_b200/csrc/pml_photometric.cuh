@@ -55,6 +55,7 @@ struct PhotoParams {
     int f_base;       // first frame of the pair handled by this launch
     int pair_n;       // frames in the pair: 1 or 2
     float* rp;        // [n_pass][S][B][H][W] reprojection losses (written in mode 1, read in mode 3)
+    uint8_t* presel;  // [n_pass][B][H][W] select_prepass_kernel: best candidate ahead of the last pair (its value: rp slot f_base)
     float* part;      // [n_cta][part_stride]: loss partial, then S x 12 dL/dP partials
     int part_stride;
     float inv_n;      // 1 / (B*H*W)
@@ -628,7 +629,7 @@ struct FinalizeParams {
 __global__ void __launch_bounds__(256)
 finalize_image_kernel(const FinalizeParams q) {
     __shared__ float s_col[1 + 12 * PML_MAX_SOURCES];
-    __shared__ float s_seg[2][128];
+    __shared__ float s_seg[256];       // flat [segment][column]: 8 x 32 or 2 x 128
     __shared__ float s_w[8][3];
     const int tid = threadIdx.x, b = blockIdx.x, pi = blockIdx.y;
     const int ncol = q.with_grad ? 1 + 12 * q.S : 1;
@@ -644,13 +645,13 @@ finalize_image_kernel(const FinalizeParams q) {
             const float* base = q.part + (size_t)(pi * q.cta_per_pass + b * q.cta_per_image) * q.part_stride + col;
             for (int c = seg; c < q.cta_per_image; c += nseg) v += base[(size_t)c * q.part_stride];
         }
-        s_seg[0][tid] = v;     // flat [segment][column]: 8 x 32 or 2 x 128
+        s_seg[tid] = v;
     }
     __syncthreads();
     if (tid < ncol) {
         float t = 0.f;
-        if (narrow) { for (int g = 0; g < 8; ++g) t += s_seg[0][g * 32 + tid]; }
-        else t = s_seg[0][tid] + s_seg[0][128 + tid];
+        if (narrow) { for (int g = 0; g < 8; ++g) t += s_seg[g * 32 + tid]; }
+        else t = s_seg[tid] + s_seg[128 + tid];
         s_col[tid] = t;
     }
     // smoothness partials of this image

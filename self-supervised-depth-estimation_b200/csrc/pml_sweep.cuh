@@ -33,6 +33,7 @@ constexpr int kSweepTW = 28;      // owned columns per strip
 constexpr int kSweepRingQ = 7;    // float4 per lane per ring slot
 constexpr int kSweepRingSlots = 4;   // rows r .. r-3 (the adjoint of row r-3 runs while row r's taps are in flight)
 constexpr int kSweepWarpFloats = 48 + 32 + kSweepRingSlots * kSweepRingQ * 4 * 32;   // P/IK, staging row, ring
+constexpr int kSweepFwdCtas = 16;  // forward-only sweeps: registers capped for 16 resident warps per SM (they have no adjoint work to hide the gathers behind)
 
 // ---- packed fp32x2 helpers (FFMA2 / FMUL2 / FADD2 on sm_100a) -----------------------------------
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
@@ -149,7 +150,7 @@ __device__ __noinline__ void sweep_flush_row(float* sG, float* gd_row, float h, 
 // in-kernel tie-break noise, no predictive mask) with its run-time flags folded into constants; the
 // generic instantiation serves the rest.
 template <bool GRAD, bool SSIM, int MODE, bool EMIT, bool COMMON = false>
-__global__ void __launch_bounds__(kSweepWarps * 32)
+__global__ void __launch_bounds__(kSweepWarps * 32, GRAD ? 1 : kSweepFwdCtas)
 sweep_kernel(const PhotoParams p) {
     PML_DYN_SMEM(float, smem);
     // grid = (n_chunks * n_strips, B, n_pass): image and pass come straight from blockIdx, so every
@@ -347,6 +348,15 @@ sweep_kernel(const PhotoParams p) {
                 if (n_id > 1) nzv1 = __ldg(at(nc, plane));
             }
         }
+        // multi-frame selection, default flags: the best candidate ahead of this pair (select_prepass_kernel)
+        float ob = 0.f;
+        int oi = 0;
+        if (COMMON && MODE == 3) {
+            const int o = clampi(py, 0, H - 1) * W + rx;
+            ob = __ldg(p.rp + ((size_t)(pass_i * S + fa) * p.B + b) * plane + o);
+            oi = __ldg(p.presel + (size_t)(pass_i * p.B + b) * plane + o);
+        }
+        if (MODE == 2) oi = ps.argmin[bp + clampi(py, 0, H - 1) * W + rx];   // the selection made by the mode-3 sweep
 
         const float sigma = fmaf(p.disp_range, d, p.min_disp);   // layers.py:23
         const float D = rcp_nr(sigma);                            // layers.py:24
@@ -585,12 +595,26 @@ sweep_kernel(const PhotoParams p) {
         } else if (mode == 2) {
             // ... adjoint sweep of an earlier pair: the selection was made by the last pair's sweep (mode 3)
             if (p_valid) {
-                const int idx = ps.argmin[bp + py * W + cx];
+                const int idx = oi;
                 if (avg) wgt = (idx == n_sel) ? f2(1.0f / (float)S, two ? 1.0f / (float)S : 0.f) : splat(0.f);
                 else wgt = f2(idx == n_sel + fa ? 1.f : 0.f, (two && idx == n_sel + fb) ? 1.f : 0.f);
                 if (fw_g != nullptr) {   // predictive mask (trainer.py:579): d (rp * m) / d rp = m
                     const float* mq = at(fw_g, (b * S + fa) * plane + py * W + cx);
                     wgt = mul2(wgt, f2(__ldg(mq), two ? __ldg(at(mq, plane)) : 0.f));
+                }
+            }
+        } else if (COMMON && mode == 3) {
+            // identity candidates and the frames of the earlier pairs were reduced by select_prepass_kernel (in the
+            // reference's order); this pair's frames come last, so they win on strictly smaller only
+            if (p_valid) {
+                float best = ob;
+                int best_i = oi;
+                if (rp.x < best) { best = rp.x; best_i = n_sel + fa; }
+                if (two && rp.y < best) { best = rp.y; best_i = n_sel + fb; }
+                wgt = f2(best_i == n_sel + fa ? 1.f : 0.f, (two && best_i == n_sel + fb) ? 1.f : 0.f);
+                if (col_owned && py >= y0 && py < y1) {
+                    loss_acc += best;
+                    ps.argmin[bp + py * W + cx] = (uint8_t)best_i;
                 }
             }
         } else if (mode == 3) {
@@ -741,6 +765,65 @@ sweep_kernel(const PhotoParams p) {
     }
 }
 
-inline size_t sweep_smem_bytes() { return (size_t)kSweepWarps * kSweepWarpFloats * sizeof(float) + 16; }
+// ---------------------------------------------------------------------------------------------
+// More than two source frames, default flags: the candidates that do not belong to the last frame pair
+// (identity losses + tie-break noise, trainer.py:592-597, and the reprojection losses the mode-1 sweeps
+// stored) are reduced here, one thread per pixel, to the first minimum in the reference's candidate order.
+// The mode-3 sweep then reads one value and one index per pixel a row step ahead instead of
+// S + f_base dependent loads at the point of use.  value -> rp slot f_base (unused by mode 1), index -> presel.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) select_prepass_kernel(const PhotoParams p) {
+    const int plane = p.H * p.W;
+    const int b = blockIdx.y, pass_i = blockIdx.z;
+    const int pix = blockIdx.x * 256 + threadIdx.x;
+    if (pix >= plane) return;
+    const int S = p.S, fa = p.f_base;
+    float* rq = p.rp + ((size_t)(pass_i * S) * p.B + b) * plane + pix;   // frame stride: B * plane
+    const float* iq = p.identity + (size_t)b * S * plane + pix;
+    // every candidate load is issued before the first comparison (predicated, fully unrolled): one round trip
+    // to memory per thread instead of S + f_base dependent ones
+    float idv[PML_MAX_SOURCES], rv[PML_MAX_SOURCES - 2];
+#pragma unroll
+    for (int i = 0; i < PML_MAX_SOURCES; ++i) idv[i] = (i < S) ? __ldg(iq + (size_t)i * plane) : 3.0e38f;
+#pragma unroll
+    for (int f = 0; f < PML_MAX_SOURCES - 2; ++f) rv[f] = (f < fa) ? rq[(size_t)f * p.B * plane] : 3.0e38f;
+    float best = 3.0e38f;
+    int best_i = 0;
+#pragma unroll
+    for (int f = 0; f < PML_MAX_SOURCES - 2; ++f)
+        if (rv[f] < best) { best = rv[f]; best_i = S + f; }
+    float m_id = 3.0e38f;
+#pragma unroll
+    for (int i = 0; i < PML_MAX_SOURCES; ++i) m_id = fminf(m_id, idv[i]);
+    // bounded in-kernel noise (|n| * 1e-5 <= 6.66e-5): an identity candidate further than 1.4e-4 above `best`
+    // cannot win against it, nor against anything smaller the last pair may still bring
+    if (m_id - best < 1.4e-4f) {
+        float ib = 3.0e38f;
+        int ib_i = 0;
+        const unsigned long long sd = p.seed_dev ? (p.seed ^ __ldg(p.seed_dev)) : p.seed;
+#pragma unroll
+        for (int i = 0; i < PML_MAX_SOURCES; i += 2) {
+            if (i < S) {
+                float n0, n1;
+                philox2_normal2((uint32_t)sd ^ ((uint32_t)(sd >> 32) * 0x9E3779B9u), (uint32_t)(b * plane + pix),
+                                (uint32_t)pass_i + 0x10000u * (uint32_t)(i >> 1), n0, n1);
+                const float c0 = fmaf(n0, kTieNoise, idv[i]);
+                if (c0 < ib) { ib = c0; ib_i = i; }
+                if (i + 1 < S) {
+                    const float c1 = fmaf(n1, kTieNoise, idv[i + 1]);
+                    if (c1 < ib) { ib = c1; ib_i = i + 1; }
+                }
+            }
+        }
+        if (ib <= best) { best = ib; best_i = ib_i; }   // identity candidates precede the reprojection ones
+    }
+    rq[(size_t)fa * p.B * plane] = best;
+    p.presel[(size_t)(pass_i * p.B + b) * plane + pix] = (uint8_t)best_i;
+}
+
+// forward-only sweeps use neither the adjoint ring nor the upsample staging row
+inline size_t sweep_smem_bytes(bool grad) {
+    return (size_t)kSweepWarps * (grad ? kSweepWarpFloats : 80) * sizeof(float) + 16;
+}
 
 }  // namespace pml
