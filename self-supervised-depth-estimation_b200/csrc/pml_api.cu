@@ -193,25 +193,37 @@ Plan make_plan(const pml_problem* p, bool grad) {
     // ceil(items / (SMs * slots)) waves of (TH + 5) row steps (5 halo steps per chunk): pick the chunk count that
     // minimises that; among equals the shorter chunks (more items: better balance, more parallelism for small
     // problems).  Measured at the headline size (profiles/r02_ab_timings.txt): 1 chunk 0.3604 ms, 2 chunks 0.3672, 3: 0.3705.
-    auto sweep_rows = [&](int slots) {
+    // More than two frames: the sweeps with adjoint are the last pair's (mode 3: 8 slots, or 12 for a lone last frame
+    // at ~0.7 of a pair's cost per row step) and one per earlier pair (mode 2); they share the chunk geometry because
+    // they share the partials.  Measured at BASELINE config 3 (37 x 8 x 4 = 1184 items per chunk = exactly one full
+    // wave): 1 chunk 1.80 ms, 2: 1.65, 3: 1.63, 5: 1.64 -- full waves hide no imbalance, which the extra quarter wave
+    // in the multi-frame cost stands for.
+    const int n_pairs = (p->S + 1) / 2;
+    const bool lone_last = (p->S > 2) && (p->S & 1);
+    auto sweep_rows = [&](int slots, bool multi = false) {
         if (knobs().th > 0) return knobs().th > p->H ? p->H : (knobs().th < 4 ? 4 : knobs().th);
         const long long cap = (long long)kNumSM * slots;
-        long long best_cost = -1;
+        double best_cost = -1;
         int best_th = p->H;
         for (int chunks = 1; chunks <= 64; ++chunks) {
             int th = (p->H + chunks - 1) / chunks;
             th = ((th + 7) / 8) * 8;
             if (th > p->H) th = p->H;
-            if (th < 16 && chunks > 1) break;
+            if (th < (multi ? 96 : 16) && chunks > 1) break;   // multi-frame, 192x640, 5 frames: 96 rows 1.445 ms, 64 rows 1.529
             const int n_ch = (p->H + th - 1) / th;
             const long long items = (long long)per_chunk * n_ch;
-            const long long cost = ((items + cap - 1) / cap) * (th + 5);
+            double waves = (double)((items + cap - 1) / cap);
+            if (multi) {
+                const long long cap3 = (long long)kNumSM * (lone_last ? kSweepLoneCtas : slots);
+                waves = (n_pairs - 1) * (waves + 0.25) + (lone_last ? 0.7 : 1.0) * ((double)((items + cap3 - 1) / cap3) + 0.25);
+            }
+            const double cost = waves * (th + 5);
             if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best_th = th; }
         }
         return best_th;
     };
     pl.TH_fwd = pl.sweep ? sweep_rows(kSweepFwdCtas) : chunk_rows(kNumSM * 6);
-    pl.TH = (pl.sweep && !grad) ? pl.TH_fwd : (pl.sweep ? sweep_rows(8) : chunk_rows(kNumSM * 6));
+    pl.TH = (pl.sweep && !grad) ? pl.TH_fwd : (pl.sweep ? sweep_rows(8, p->S > 2) : chunk_rows(kNumSM * 6));
     pl.n_chunks = (p->H + pl.TH - 1) / pl.TH;
     pl.n_chunks_fwd = (p->H + pl.TH_fwd - 1) / pl.TH_fwd;
     pl.cta_per_pass = p->B * pl.n_chunks * pl.n_strips;
@@ -284,7 +296,8 @@ bool sweep_common(const PhotoParams& pp) {
 
 template <bool GRAD, bool SSIM>
 int launch_sweep(const PhotoParams& pp, cudaStream_t st) {
-    const size_t smem = sweep_smem_bytes(GRAD && pp.mode != 1) + (size_t)(GRAD ? knobs().smem_pad : 0);   // < 48 KB: no opt-in needed
+    const bool lone = pp.mode == 3 && pp.pair_n == 1;   // single last frame: scalar instantiation, shorter ring
+    const size_t smem = sweep_smem_bytes(GRAD && pp.mode != 1, !lone) + (size_t)(GRAD ? knobs().smem_pad : 0);   // < 48 KB: no opt-in needed
     if (pp.B > 65535) return PML_ERR_UNSUPPORTED;
     const dim3 grid(pp.n_chunks * pp.n_strips, pp.B, pp.n_pass);
     bool emit = false;   // by-products requested by any pass (never in sweep mode 2)
@@ -296,6 +309,10 @@ int launch_sweep(const PhotoParams& pp, cudaStream_t st) {
         if (common)    PML_LAUNCH((sweep_kernel<GRAD, SSIM, 0, false, true>), grid, blk, smem, st, pp);
         else if (emit) PML_LAUNCH((sweep_kernel<GRAD, SSIM, 0, true>), grid, blk, smem, st, pp);
         else           PML_LAUNCH((sweep_kernel<GRAD, SSIM, 0, false>), grid, blk, smem, st, pp);
+    } else if (lone) {
+        if (common)    PML_LAUNCH((sweep_kernel<GRAD, SSIM, 3, false, true, false>), grid, blk, smem, st, pp);
+        else if (emit) PML_LAUNCH((sweep_kernel<GRAD, SSIM, 3, true, false, false>), grid, blk, smem, st, pp);
+        else           PML_LAUNCH((sweep_kernel<GRAD, SSIM, 3, false, false, false>), grid, blk, smem, st, pp);
     } else if (pp.mode == 3) {
         if (common)    PML_LAUNCH((sweep_kernel<GRAD, SSIM, 3, false, true>), grid, blk, smem, st, pp);
         else if (emit) PML_LAUNCH((sweep_kernel<GRAD, SSIM, 3, true>), grid, blk, smem, st, pp);
