@@ -223,7 +223,7 @@ Plan make_plan(const pml_problem* p, bool grad) {
         return best_th;
     };
     pl.TH_fwd = pl.sweep ? sweep_rows(kSweepFwdCtas) : chunk_rows(kNumSM * 6);
-    pl.TH = (pl.sweep && !grad) ? pl.TH_fwd : (pl.sweep ? sweep_rows(8, p->S > 2) : chunk_rows(kNumSM * 6));
+    pl.TH = (pl.sweep && !grad) ? pl.TH_fwd : (pl.sweep ? sweep_rows(p->S == 1 ? kSweepLoneCtas : 8, p->S > 2) : chunk_rows(kNumSM * 6));
     pl.n_chunks = (p->H + pl.TH - 1) / pl.TH;
     pl.n_chunks_fwd = (p->H + pl.TH_fwd - 1) / pl.TH_fwd;
     pl.cta_per_pass = p->B * pl.n_chunks * pl.n_strips;
@@ -296,7 +296,8 @@ bool sweep_common(const PhotoParams& pp) {
 
 template <bool GRAD, bool SSIM>
 int launch_sweep(const PhotoParams& pp, cudaStream_t st) {
-    const bool lone = pp.mode == 3 && pp.pair_n == 1;   // single last frame: scalar instantiation, shorter ring
+    // a single frame (the last one of an odd count; stereo-only training: S = 1): scalar instantiation, shorter ring
+    const bool lone = (pp.mode == 3 || pp.mode == 0) && pp.pair_n == 1;
     const size_t smem = sweep_smem_bytes(GRAD && pp.mode != 1, !lone) + (size_t)(GRAD ? knobs().smem_pad : 0);   // < 48 KB: no opt-in needed
     if (pp.B > 65535) return PML_ERR_UNSUPPORTED;
     const dim3 grid(pp.n_chunks * pp.n_strips, pp.B, pp.n_pass);
@@ -305,10 +306,13 @@ int launch_sweep(const PhotoParams& pp, cudaStream_t st) {
     const dim3 blk(kSweepWarps * 32);
     if (pp.mode == 2) emit = false;   // the adjoint sweeps of earlier pairs never write by-products
     const bool common = sweep_common(pp);
-    if (pp.mode == 0) {
+    if (pp.mode == 0 && !lone) {
         if (common)    PML_LAUNCH((sweep_kernel<GRAD, SSIM, 0, false, true>), grid, blk, smem, st, pp);
         else if (emit) PML_LAUNCH((sweep_kernel<GRAD, SSIM, 0, true>), grid, blk, smem, st, pp);
         else           PML_LAUNCH((sweep_kernel<GRAD, SSIM, 0, false>), grid, blk, smem, st, pp);
+    } else if (lone && pp.mode == 0) {
+        if (emit)      PML_LAUNCH((sweep_kernel<GRAD, SSIM, 0, true, false, false>), grid, blk, smem, st, pp);
+        else           PML_LAUNCH((sweep_kernel<GRAD, SSIM, 0, false, false, false>), grid, blk, smem, st, pp);
     } else if (lone) {
         if (common)    PML_LAUNCH((sweep_kernel<GRAD, SSIM, 3, false, true, false>), grid, blk, smem, st, pp);
         else if (emit) PML_LAUNCH((sweep_kernel<GRAD, SSIM, 3, true, false, false>), grid, blk, smem, st, pp);

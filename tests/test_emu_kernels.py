@@ -60,6 +60,20 @@ PHILOX_CASES = [((-1, 1), 64, 160), ((-1, 1, "s"), 32, 64), ((-1, 1, -2, 2), 32,
                 ((-1, 1, -2, 2, -3, 3, -4, 4), 32, 64)]
 
 
+@pytest.mark.parametrize("noise_seed", [7, None])
+def test_stereo_only_single_source(emu_lib, noise_seed):
+    """Stereo-only training (frame_ids [0] + "s": one source frame) runs the scalar single-frame instantiation
+    sweep_kernel<.., MODE=0, .., PAIR=false>; with host noise and by-products, and with in-kernel noise."""
+    B, H, W = 2, 32, 64
+    opt = synthetic.make_options(H, W, batch_size=B)
+    inputs, outputs = synthetic.make_batch(B, H, W, sources=("s",), seed=8)
+    extra = {} if noise_seed is not None else dict(pml_emit_warped=False, pml_emit_depth="scale0")
+    got = common.run_product(opt, inputs, outputs, "trainer", device="cpu", noise_seed=noise_seed, sources=("s",),
+                             extra_opt=extra)
+    parity.check(got, opt, "trainer", inputs, outputs, noise_seed or 0, sources=("s",), philox=noise_seed is None,
+                 loss_tol=parity.LOSS_TOL_SMALL)
+
+
 @pytest.mark.parametrize("sources,H,W", PHILOX_CASES)
 def test_default_training_instantiation(emu_lib, sources, H, W):
     """The configuration bench.py times and trainer_hooks runs by default: tie-break noise drawn in-kernel

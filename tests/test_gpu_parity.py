@@ -67,7 +67,10 @@ def test_against_oracle(cuda_lib, name):
 
 
 PHILOX_CASES = {
-    # (sources, B, H, W): mode 0 at the headline resolution, modes 1/3/2 with three, four and eight frames
+    # (sources, B, H, W): mode 0 at the headline resolution, modes 1/3/2 with three, four and eight frames,
+    # stereo-only training (one source frame: the scalar single-frame instantiation)
+    "s1_stereo_96x320": (("s",), 2, 96, 320),
+    "s5_64x160": ((-1, 1, -2, 2, "s"), 2, 64, 160),
     "s2_192x640": ((-1, 1), 2, 192, 640),
     "s2_odd_72x200": ((-1, 1), 3, 72, 200),
     "s3_stereo_96x320": ((-1, 1, "s"), 2, 96, 320),
