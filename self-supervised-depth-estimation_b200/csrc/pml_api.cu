@@ -482,8 +482,12 @@ int run_loss(const pml_problem* p, void* ws, size_t ws_bytes, cudaStream_t st, b
         if (rc == PML_OK) {
             pp.mode = 3; pp.f_base = last_fa; pp.pair_n = (last_fa + 1 < p->S) ? 2 : 1;
             pp.presel = reinterpret_cast<uint8_t*>(base + pl.off_presel);
-            if (sweep_common(pp))   // candidates ahead of the last pair -> one value + one index per pixel
-                PML_LAUNCH(select_prepass_kernel, dim3((p->H * p->W + 255) / 256, p->B, p->n_pass), dim3(256), 0, st, pp);
+            if (sweep_common(pp)) {   // candidates ahead of the last pair -> one value + one index per pixel
+                const dim3 g((p->H * p->W + 255) / 256, p->B);
+                if (last_fa == 2)      PML_LAUNCH(select_prepass_kernel<2>, g, dim3(256), 0, st, pp);
+                else if (last_fa == 4) PML_LAUNCH(select_prepass_kernel<4>, g, dim3(256), 0, st, pp);
+                else                   PML_LAUNCH(select_prepass_kernel<6>, g, dim3(256), 0, st, pp);
+            }
             if (grad) rc = ssim ? launch_sweep<true, true>(pp, st) : launch_sweep<true, false>(pp, st);
             else      rc = ssim ? launch_sweep<false, true>(pp, st) : launch_sweep<false, false>(pp, st);
         }

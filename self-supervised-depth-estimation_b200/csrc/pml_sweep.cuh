@@ -829,62 +829,67 @@ sweep_kernel(const PhotoParams p) {
 // The mode-3 sweep then reads one value and one index per pixel a row step ahead instead of
 // S + f_base dependent loads at the point of use.  value -> rp slot f_base (unused by mode 1), index -> presel.
 // ---------------------------------------------------------------------------------------------
+// NF = f_base (frames swept before the last pair: 2, 4 or 6), S = NF + 1 or NF + 2.  One thread per pixel does all
+// passes (scales): the identity candidates and their two smallest values are the same for every pass.
+template <int NF>
 __global__ void __launch_bounds__(256) select_prepass_kernel(const PhotoParams p) {
     const int plane = p.H * p.W;
-    const int b = blockIdx.y, pass_i = blockIdx.z;
+    const int b = blockIdx.y;
     const int pix = blockIdx.x * 256 + threadIdx.x;
     if (pix >= plane) return;
-    const int S = p.S, fa = p.f_base;
-    float* rq = p.rp + ((size_t)(pass_i * S) * p.B + b) * plane + pix;   // frame stride: B * plane
+    const int S = p.S;
     const float* iq = p.identity + (size_t)b * S * plane + pix;
-    // every candidate load is issued before the first comparison (predicated, fully unrolled): one round trip
-    // to memory per thread instead of S + f_base dependent ones
-    float idv[PML_MAX_SOURCES], rv[PML_MAX_SOURCES - 2];
+    float idv[NF + 2];
 #pragma unroll
-    for (int i = 0; i < PML_MAX_SOURCES; ++i) idv[i] = (i < S) ? __ldg(iq + (size_t)i * plane) : 3.0e38f;
-#pragma unroll
-    for (int f = 0; f < PML_MAX_SOURCES - 2; ++f) rv[f] = (f < fa) ? rq[(size_t)f * p.B * plane] : 3.0e38f;
-    float best = 3.0e38f;
-    int best_i = 0;
-#pragma unroll
-    for (int f = 0; f < PML_MAX_SOURCES - 2; ++f)
-        if (rv[f] < best) { best = rv[f]; best_i = S + f; }
+    for (int i = 0; i < NF + 1; ++i) idv[i] = __ldg(at(iq, i * plane));
+    idv[NF + 1] = (S > NF + 1) ? __ldg(at(iq, (NF + 1) * plane)) : 3.0e38f;
     float m1 = 3.0e38f, m2 = 3.0e38f;   // smallest and second smallest identity candidate
     int i1 = 0;
 #pragma unroll
-    for (int i = 0; i < PML_MAX_SOURCES; ++i) {
+    for (int i = 0; i < NF + 2; ++i) {
         const float v = idv[i];
         m2 = fminf(m2, fmaxf(v, m1));
         if (v < m1) { m1 = v; i1 = i; }
     }
-    // The in-kernel noise is bounded (|n| * 1e-5 <= 6.66e-5), so it can only decide between candidates closer than
-    // 1.4e-4: two identity candidates, or the smallest of them and `best`.  Elsewhere the generator is skipped and
-    // the tie-break noise is 0, exactly like the gate of the two-frame sweep (sweep_kernel, mode 0); against the last
-    // pair's frames (compared in the mode-3 sweep) an unambiguous identity winner enters with noise 0 as well.
-    if ((m1 - best < 1.4e-4f) && ((m2 - m1 < 1.4e-4f) || (best - m1 < 1.4e-4f))) {
-        float ib = 3.0e38f;
-        int ib_i = 0;
-        const unsigned long long sd = p.seed_dev ? (p.seed ^ __ldg(p.seed_dev)) : p.seed;
+    const size_t fstride = (size_t)p.B * plane;     // frame stride of rp
+    float* rq = p.rp + (size_t)b * plane + pix;
+    uint8_t* sq = p.presel + (size_t)b * plane + pix;
+#pragma unroll 1
+    for (int pass_i = 0; pass_i < p.n_pass; ++pass_i, rq += S * fstride, sq += fstride) {
+        // every load is issued before the first comparison: one round trip to memory per pass
+        float rv[NF];
 #pragma unroll
-        for (int i = 0; i < PML_MAX_SOURCES; i += 2) {
-            if (i < S) {
+        for (int f = 0; f < NF; ++f) rv[f] = rq[f * fstride];
+        float best = 3.0e38f;
+        int best_i = 0;
+#pragma unroll
+        for (int f = 0; f < NF; ++f)
+            if (rv[f] < best) { best = rv[f]; best_i = S + f; }
+        // The in-kernel noise is bounded (|n| * 1e-5 <= 6.66e-5), so it can only decide between candidates closer than
+        // 1.4e-4: two identity candidates, or the smallest of them and `best`.  Elsewhere the generator is skipped and
+        // the tie-break noise is 0, exactly like the gate of the two-frame sweep (sweep_kernel, mode 0); against the
+        // last pair's frames (compared in the mode-3 sweep) an unambiguous identity winner enters with noise 0 as well.
+        if ((m1 - best < 1.4e-4f) && ((m2 - m1 < 1.4e-4f) || (best - m1 < 1.4e-4f))) {
+            float ib = 3.0e38f;
+            int ib_i = 0;
+            const unsigned long long sd = p.seed_dev ? (p.seed ^ __ldg(p.seed_dev)) : p.seed;
+#pragma unroll
+            for (int i = 0; i < NF + 2; i += 2) {
                 float n0, n1;
                 philox2_normal2((uint32_t)sd ^ ((uint32_t)(sd >> 32) * 0x9E3779B9u), (uint32_t)(b * plane + pix),
                                 (uint32_t)pass_i + 0x10000u * (uint32_t)(i >> 1), n0, n1);
                 const float c0 = fmaf(n0, kTieNoise, idv[i]);
                 if (c0 < ib) { ib = c0; ib_i = i; }
-                if (i + 1 < S) {
-                    const float c1 = fmaf(n1, kTieNoise, idv[i + 1]);
-                    if (c1 < ib) { ib = c1; ib_i = i + 1; }
-                }
+                const float c1 = fmaf(n1, kTieNoise, idv[i + 1]);     // a missing last candidate stays at 3e38
+                if (c1 < ib) { ib = c1; ib_i = i + 1; }
             }
+            if (ib <= best) { best = ib; best_i = ib_i; }   // identity candidates precede the reprojection ones
+        } else if (m1 < best) {
+            best = m1; best_i = i1;
         }
-        if (ib <= best) { best = ib; best_i = ib_i; }   // identity candidates precede the reprojection ones
-    } else if (m1 < best) {
-        best = m1; best_i = i1;
+        rq[NF * fstride] = best;
+        *sq = (uint8_t)best_i;
     }
-    rq[(size_t)fa * p.B * plane] = best;
-    p.presel[(size_t)(pass_i * p.B + b) * plane + pix] = (uint8_t)best_i;
 }
 
 // forward-only sweeps use neither the adjoint ring nor the upsample staging row
