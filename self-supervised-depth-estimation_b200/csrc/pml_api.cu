@@ -223,7 +223,7 @@ Plan make_plan(const pml_problem* p, bool grad) {
         return best_th;
     };
     pl.TH_fwd = pl.sweep ? sweep_rows(kSweepFwdCtas) : chunk_rows(kNumSM * 6);
-    pl.TH = (pl.sweep && !grad) ? pl.TH_fwd : (pl.sweep ? sweep_rows(p->S == 1 ? kSweepLoneCtas : 8, p->S > 2) : chunk_rows(kNumSM * 6));
+    pl.TH = (pl.sweep && !grad) ? pl.TH_fwd : (pl.sweep ? sweep_rows(p->S == 1 ? kSweepLoneCtas : kSweepPairCtas, p->S > 2) : chunk_rows(kNumSM * 6));
     pl.n_chunks = (p->H + pl.TH - 1) / pl.TH;
     pl.n_chunks_fwd = (p->H + pl.TH_fwd - 1) / pl.TH_fwd;
     pl.cta_per_pass = p->B * pl.n_chunks * pl.n_strips;

@@ -36,6 +36,11 @@ constexpr int kSweepRingSlots = 4;   // rows r .. r-3 (the adjoint of row r-3 ru
 constexpr int kSweepWarpFloats = 48 + 32 + kSweepRingSlots * kSweepRingQ * 4 * 32;   // P/IK, staging row, ring
 constexpr int kSweepFwdCtas = 16;  // forward-only sweeps: registers capped for 16 resident warps per SM (they have no adjoint work to hide the gathers behind)
 constexpr int kSweepLoneCtas = 12; // single-frame sweeps with adjoint: scalar arithmetic fits 168 registers without spills
+// register budget of the forward+backward sweep of a frame pair and the resident warps per SM it allows
+#ifndef PML_SWEEP_REGS
+#define PML_SWEEP_REGS 255
+#endif
+constexpr int kSweepPairCtas = 65536 / (((PML_SWEEP_REGS * 32 + 511) / 512) * 512);
 
 // ---- packed fp32x2 helpers (FFMA2 / FMUL2 / FADD2 on sm_100a) -----------------------------------
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
@@ -189,7 +194,7 @@ __device__ __noinline__ void sweep_flush_row(float* sG, float* gd_row, float h, 
 // generic instantiation serves the rest.
 // PAIR = false: the launch sweeps a single frame (the last one of an odd frame count) with scalar arithmetic.
 template <bool GRAD, bool SSIM, int MODE, bool EMIT, bool COMMON = false, bool PAIR = true>
-__global__ void __launch_bounds__(kSweepWarps * 32, GRAD ? (PAIR ? 1 : kSweepLoneCtas) : kSweepFwdCtas)
+__global__ void __maxnreg__(GRAD ? (PAIR ? PML_SWEEP_REGS : 168) : 128)
 sweep_kernel(const PhotoParams p) {
     PML_DYN_SMEM(float, smem);
     PML_PACKED_OPS(PAIR);

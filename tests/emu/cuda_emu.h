@@ -27,6 +27,7 @@
 #define __forceinline__ inline
 #define __noinline__
 #define __launch_bounds__(...)
+#define __maxnreg__(...)
 #define __shared__ static thread_local   /* one block at a time per OS thread */
 #define __align__(n)
 #define __restrict__ __restrict

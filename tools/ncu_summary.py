@@ -1,9 +1,13 @@
-"""Summarise one kernel of an .ncu-rep (ncu --set full) into the text form kept under profiles/.
-    python tools/ncu_summary.py <report.ncu-rep> "<header line>" > profiles/<name>.txt"""
+"""Summarise one kernel of an .ncu-rep (ncu --set full) -- or of its `--page raw --csv` export -- into the text
+form kept under profiles/.
+    python tools/ncu_summary.py <report.ncu-rep | raw.csv> "<header line>" [launch index] > profiles/<name>.txt"""
 import csv, subprocess, sys
-out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(out.splitlines()))
-hdr, units, vals = rows[0], rows[1], rows[2]
+if sys.argv[1].endswith(".csv"):
+    out = open(sys.argv[1]).read()
+else:
+    out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(l for l in out.splitlines() if l.startswith('"')))
+hdr, units, vals = rows[0], rows[1], rows[2 + (int(sys.argv[3]) if len(sys.argv) > 3 else 0)]
 d = dict(zip(hdr, zip(vals, units)))
 print("# " + sys.argv[2])
 print("# kernel: " + d["Kernel Name"][0])
