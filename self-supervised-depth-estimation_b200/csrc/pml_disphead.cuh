@@ -171,6 +171,206 @@ disp_head_bwd_kernel(const HeadParams p) {
     if (lane == 0) out[9] = vb;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Tile kernels for the large heads (scales 0 and 1: few channels, many pixels).  The warp march above keeps one row of
+// loads in flight per warp, which leaves the two big heads latency-bound at < 1 TB/s; here every thread owns a column
+// of four output rows, addresses its 6 x 3 neighbourhood directly (L1 serves the horizontal and vertical overlap), and
+// has all 18 loads of a channel in flight at once.  Block = 32 x 8 threads = a 32 x 32 pixel tile.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kHeadTileRows = 4;    // output rows per thread
+
+struct HeadTileIdx {
+    int ro[kHeadTileRows + 2];   // row offsets (reflected, clamped into the image) of rows q0-1 .. q0+4
+    int co[3];                   // column offsets of cx-1, cx, cx+1 (reflected)
+    int cx, q0;
+    bool col_ok;
+};
+__device__ __forceinline__ HeadTileIdx head_tile_idx(int h, int w) {
+    HeadTileIdx t;
+    t.cx = blockIdx.x * 32 + (threadIdx.x & 31);
+    t.q0 = blockIdx.y * (8 * kHeadTileRows) + (threadIdx.x >> 5) * kHeadTileRows;
+    t.col_ok = t.cx < w;
+    const int cxc = min(t.cx, w - 1);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) t.co[k] = reflect1(cxc + k - 1, w);
+#pragma unroll
+    for (int j = 0; j < kHeadTileRows + 2; ++j) t.ro[j] = reflect1(min(t.q0 - 1 + j, h), h) * w;   // row h reflects to h-2
+    return t;
+}
+
+// forward: grid = (ceil(w/32), ceil(h/32), B); dynamic smem = C * 12 floats
+__global__ void __launch_bounds__(256)
+disp_head_fwd_tile_kernel(const HeadParams p) {
+    PML_DYN_SMEM(float, sw);
+    const int C = p.C, h = p.h, w = p.w, plane = h * w;
+    for (int i = threadIdx.x; i < C * 9; i += blockDim.x) sw[(i / 9) * 12 + (i % 9)] = p.weight[i];
+    __syncthreads();
+    const HeadTileIdx t = head_tile_idx(h, w);
+    const int b = blockIdx.z;
+    const float* xc = p.x + (size_t)b * C * plane;
+    float a[kHeadTileRows];
+#pragma unroll
+    for (int i = 0; i < kHeadTileRows; ++i) a[i] = 0.f;
+#pragma unroll 2
+    for (int c = 0; c < C; ++c, xc += plane) {
+        float v[kHeadTileRows + 2][3];
+#pragma unroll
+        for (int j = 0; j < kHeadTileRows + 2; ++j)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) v[j][k] = __ldg(xc + t.ro[j] + t.co[k]);
+        const float4* wk = reinterpret_cast<const float4*>(sw + c * 12);
+        const float4 w0 = wk[0], w1 = wk[1], w2 = wk[2];
+        const float W[9] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x};
+#pragma unroll
+        for (int i = 0; i < kHeadTileRows; ++i)
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) a[i] = fmaf(W[dy * 3 + k], v[i + dy][k], a[i]);
+    }
+    const float bias = __ldg(p.bias);
+    if (t.col_ok) {
+#pragma unroll
+        for (int i = 0; i < kHeadTileRows; ++i)
+            if (t.q0 + i < h) p.disp[(size_t)b * plane + (t.q0 + i) * w + t.cx] = sigmoidf(a[i] + bias);
+    }
+}
+
+// backward, input gradient: same tiling.  The folded gz neighbourhood of the four output rows (see the comment of
+// disp_head_bwd_kernel) is computed once per thread and serves every channel: nine FMAs and one store per channel.
+__global__ void __launch_bounds__(256)
+disp_head_gx_tile_kernel(const HeadParams p) {
+    PML_DYN_SMEM(float, sw);
+    const int C = p.C, h = p.h, w = p.w, plane = h * w;
+    for (int i = threadIdx.x; i < C * 9; i += blockDim.x) sw[(i / 9) * 12 + (i % 9)] = p.weight[i];
+    __syncthreads();
+    const int cx = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int q0 = blockIdx.y * (8 * kHeadTileRows) + (threadIdx.x >> 5) * kHeadTileRows;
+    const int b = blockIdx.z;
+    const float* gd = p.g_disp + (size_t)b * plane;
+    const float* dd = p.disp + (size_t)b * plane;
+    // gz rows q0-1 .. q0+4, columns cx-1 .. cx+1, zero outside the image, column fold applied
+    float g[kHeadTileRows + 2][3];
+    const float f1 = (cx == 1) ? 1.f : 0.f, f2 = (cx == w - 2) ? 1.f : 0.f;
+#pragma unroll
+    for (int j = 0; j < kHeadTileRows + 2; ++j) {
+        const int r = q0 - 1 + j;
+        float z[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int c = cx + k - 1;
+            z[k] = 0.f;
+            if (r >= 0 && r < h && c >= 0 && c < w) {
+                const float d = __ldg(dd + r * w + c);
+                z[k] = __ldg(gd + r * w + c) * d * (1.f - d);
+            }
+        }
+        g[j][0] = z[0] + f2 * z[2]; g[j][1] = z[1]; g[j][2] = z[2] + f1 * z[0];
+    }
+    if (cx >= w) return;
+    float* gx = p.g_x + (size_t)b * C * plane + cx;
+#pragma unroll 2
+    for (int c = 0; c < C; ++c, gx += plane) {
+        const float4* wk = reinterpret_cast<const float4*>(sw + c * 12);
+        const float4 w0 = wk[0], w1 = wk[1], w2 = wk[2];
+        const float W[9] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x};
+#pragma unroll
+        for (int i = 0; i < kHeadTileRows; ++i) {
+            const int q = q0 + i;
+            const float g1 = (q == 1) ? 1.f : 0.f, g2 = (q == h - 2) ? 1.f : 0.f;
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float u = g[i][k] + g2 * g[i + 2][k], dn = g[i + 2][k] + g1 * g[i][k];
+                s = fmaf(W[6 + (2 - k)], u, fmaf(W[3 + (2 - k)], g[i + 1][k], fmaf(W[0 + (2 - k)], dn, s)));
+            }
+            if (q < h) gx[q * w] = s;
+        }
+    }
+}
+
+// backward, weight / bias gradient: the warp march, eight channels per warp.  Row r of x_pad meets the gz of the
+// windows centred on rows r+1 (tap row 0), r (tap row 1) and r-1 (tap row 2), so the per-channel state is just the
+// nine accumulators; the eight loads of row r+1 are issued before row r is consumed.
+// grid = B * ceil(C/8) * n_chunks * n_strips warps; part layout as in disp_head_bwd_kernel.
+constexpr int kHeadCB = 8;
+__global__ void __launch_bounds__(32, 12)
+disp_head_gw_kernel(const HeadParams p) {
+    const int lane = threadIdx.x;
+    const int C = p.C, h = p.h, w = p.w, plane = h * w;
+    const int n_cg = (C + kHeadCB - 1) / kHeadCB;
+    int item = blockIdx.x;
+    const int strip = item % p.n_strips; item /= p.n_strips;
+    const int chunk = item % p.n_chunks; item /= p.n_chunks;
+    const int cg = item % n_cg;
+    const int b = item / n_cg;
+    const int c0 = cg * kHeadCB;
+    const int x0 = strip * kHeadTW, x1 = min(x0 + kHeadTW, w);
+    const int y0 = chunk * kHeadTH, y1 = min(y0 + kHeadTH, h);
+    const int cx = x0 - 1 + lane;
+    const int rx = reflect1(clampi(cx, -1, w), w);
+    const bool owned = (cx >= x0) && (cx < x1);
+    const float* xb = p.x + ((size_t)b * C + c0) * plane + rx;
+    const float* gd = p.g_disp + (size_t)b * plane + min(max(cx, 0), w - 1);
+    const float* dd = p.disp + (size_t)b * plane + min(max(cx, 0), w - 1);
+    auto gz_row = [&](int r) {     // gz(r, cx) of the windows this item owns, else 0
+        float z = 0.f;
+        if (owned && r >= y0 && r < y1) {
+            const float d = __ldg(dd + r * w);
+            z = __ldg(gd + r * w) * d * (1.f - d);
+        }
+        return z;
+    };
+    auto x_row = [&](int r, float (&v)[kHeadCB]) {
+        const int ry = reflect1(clampi(r, -1, h), h);
+#pragma unroll
+        for (int k = 0; k < kHeadCB; ++k) v[k] = (c0 + k < C) ? __ldg(xb + (size_t)k * plane + ry * w) : 0.f;
+    };
+    float acc[kHeadCB][9];
+#pragma unroll
+    for (int k = 0; k < kHeadCB; ++k)
+#pragma unroll
+        for (int d = 0; d < 9; ++d) acc[k][d] = 0.f;
+    float accb = 0.f;
+    float gA = 0.f, gB = gz_row(y0 - 1), gC = gz_row(y0);   // gz of rows r-1, r, r+1 for r = y0 - 1
+    float va[kHeadCB], vb[kHeadCB];
+    x_row(y0 - 1, va);
+    auto step = [&](int r, const float (&v)[kHeadCB], float (&vn)[kHeadCB]) {
+        x_row(r + 1, vn);
+        const float gN = gz_row(r + 2);
+#pragma unroll
+        for (int k = 0; k < kHeadCB; ++k) {
+            const float l = __shfl_up_sync(0xffffffffu, v[k], 1), rr = __shfl_down_sync(0xffffffffu, v[k], 1);
+            acc[k][0] = fmaf(gC, l, acc[k][0]); acc[k][1] = fmaf(gC, v[k], acc[k][1]); acc[k][2] = fmaf(gC, rr, acc[k][2]);
+            acc[k][3] = fmaf(gB, l, acc[k][3]); acc[k][4] = fmaf(gB, v[k], acc[k][4]); acc[k][5] = fmaf(gB, rr, acc[k][5]);
+            acc[k][6] = fmaf(gA, l, acc[k][6]); acc[k][7] = fmaf(gA, v[k], acc[k][7]); acc[k][8] = fmaf(gA, rr, acc[k][8]);
+        }
+        accb += gB;
+        gA = gB; gB = gC; gC = gN;
+    };
+#pragma unroll 1
+    for (int r = y0 - 1; r <= y1; r += 2) {     // an extra step past y1 only meets gz = 0
+        step(r, va, vb);
+        step(r + 1, vb, va);
+    }
+    const int per = p.n_chunks * p.n_strips;
+    const int j = chunk * p.n_strips + strip;
+#pragma unroll
+    for (int k = 0; k < kHeadCB; ++k) {
+        if (c0 + k >= C) break;
+        float* out = p.part + ((size_t)(b * C + c0 + k) * per + j) * 10;
+#pragma unroll
+        for (int d = 0; d < 9; ++d) {
+            const float v = warp_sum(acc[k][d]);
+            if (lane == 0) out[d] = v;
+        }
+        if (k == 0) {
+            const float vb2 = warp_sum(accb);
+            if (lane == 0) out[9] = vb2;
+        }
+    }
+}
+
 // fixed-order reduction of the partials: block c sums the 9 weight gradients of channel c over (image, chunk,
 // strip); block C sums the bias gradient (taken from the items of channel 0).  256 threads.
 __global__ void __launch_bounds__(256)
