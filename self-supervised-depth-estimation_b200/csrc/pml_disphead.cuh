@@ -174,10 +174,13 @@ disp_head_bwd_kernel(const HeadParams p) {
 // ---------------------------------------------------------------------------------------------------------------
 // Tile kernels for the large heads (scales 0 and 1: few channels, many pixels).  The warp march above keeps one row of
 // loads in flight per warp, which leaves the two big heads latency-bound at < 1 TB/s; here every thread owns a column
-// of four output rows, addresses its 6 x 3 neighbourhood directly (L1 serves the horizontal and vertical overlap), and
-// has all 18 loads of a channel in flight at once.  Block = 32 x 8 threads = a 32 x 32 pixel tile.
+// of six output rows, addresses its 8 x 3 neighbourhood directly (L1 serves the horizontal and vertical overlap), and
+// has all 24 loads of a channel in flight at once.  Block = 32 x 8 threads = a 32 x 48 pixel tile (forward).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kHeadTileRows = 4;    // output rows per thread
+constexpr int kHeadTileRows = 6;    // output rows per thread, forward (a block of 32 x 8 threads covers 32 x 48 pixels)
+constexpr int kHeadGxRows = 4;      // ... input-gradient kernel (32 x 32 pixels)
+
+constexpr int kHeadTileH = 8 * kHeadTileRows, kHeadGxTileH = 8 * kHeadGxRows;   // tile heights
 
 struct HeadTileIdx {
     int ro[kHeadTileRows + 2];   // row offsets (reflected, clamped into the image) of rows q0-1 .. q0+4
@@ -199,7 +202,7 @@ __device__ __forceinline__ HeadTileIdx head_tile_idx(int h, int w) {
 }
 
 // forward: grid = (ceil(w/32), ceil(h/32), B); dynamic smem = C * 12 floats
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 disp_head_fwd_tile_kernel(const HeadParams p) {
     PML_DYN_SMEM(float, sw);
     const int C = p.C, h = p.h, w = p.w, plane = h * w;
@@ -211,7 +214,7 @@ disp_head_fwd_tile_kernel(const HeadParams p) {
     float a[kHeadTileRows];
 #pragma unroll
     for (int i = 0; i < kHeadTileRows; ++i) a[i] = 0.f;
-#pragma unroll 2
+#pragma unroll 1
     for (int c = 0; c < C; ++c, xc += plane) {
         float v[kHeadTileRows + 2][3];
 #pragma unroll
@@ -245,15 +248,15 @@ disp_head_gx_tile_kernel(const HeadParams p) {
     for (int i = threadIdx.x; i < C * 9; i += blockDim.x) sw[(i / 9) * 12 + (i % 9)] = p.weight[i];
     __syncthreads();
     const int cx = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int q0 = blockIdx.y * (8 * kHeadTileRows) + (threadIdx.x >> 5) * kHeadTileRows;
+    const int q0 = blockIdx.y * (8 * kHeadGxRows) + (threadIdx.x >> 5) * kHeadGxRows;
     const int b = blockIdx.z;
     const float* gd = p.g_disp + (size_t)b * plane;
     const float* dd = p.disp + (size_t)b * plane;
     // gz rows q0-1 .. q0+4, columns cx-1 .. cx+1, zero outside the image, column fold applied
-    float g[kHeadTileRows + 2][3];
+    float g[kHeadGxRows + 2][3];
     const float f1 = (cx == 1) ? 1.f : 0.f, f2 = (cx == w - 2) ? 1.f : 0.f;
 #pragma unroll
-    for (int j = 0; j < kHeadTileRows + 2; ++j) {
+    for (int j = 0; j < kHeadGxRows + 2; ++j) {
         const int r = q0 - 1 + j;
         float z[3];
 #pragma unroll
@@ -275,7 +278,7 @@ disp_head_gx_tile_kernel(const HeadParams p) {
         const float4 w0 = wk[0], w1 = wk[1], w2 = wk[2];
         const float W[9] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x};
 #pragma unroll
-        for (int i = 0; i < kHeadTileRows; ++i) {
+        for (int i = 0; i < kHeadGxRows; ++i) {
             const int q = q0 + i;
             const float g1 = (q == 1) ? 1.f : 0.f, g2 = (q == h - 2) ? 1.f : 0.f;
             float s = 0.f;
@@ -291,7 +294,7 @@ disp_head_gx_tile_kernel(const HeadParams p) {
 
 // backward, weight / bias gradient: the warp march, eight channels per warp.  Row r of x_pad meets the gz of the
 // windows centred on rows r+1 (tap row 0), r (tap row 1) and r-1 (tap row 2), so the per-channel state is just the
-// nine accumulators; the eight loads of row r+1 are issued before row r is consumed.
+// nine accumulators; the eight loads of row r+2 are issued before row r is consumed (two rows in flight per warp).
 // grid = B * ceil(C/8) * n_chunks * n_strips warps; part layout as in disp_head_bwd_kernel.
 constexpr int kHeadCB = 8;
 __global__ void __launch_bounds__(32, 12)
@@ -333,10 +336,11 @@ disp_head_gw_kernel(const HeadParams p) {
         for (int d = 0; d < 9; ++d) acc[k][d] = 0.f;
     float accb = 0.f;
     float gA = 0.f, gB = gz_row(y0 - 1), gC = gz_row(y0);   // gz of rows r-1, r, r+1 for r = y0 - 1
-    float va[kHeadCB], vb[kHeadCB];
+    float va[kHeadCB], vb[kHeadCB], vc[kHeadCB];     // rows r, r+1 (in flight), r+2 (issued by the step)
     x_row(y0 - 1, va);
+    x_row(y0, vb);
     auto step = [&](int r, const float (&v)[kHeadCB], float (&vn)[kHeadCB]) {
-        x_row(r + 1, vn);
+        x_row(r + 2, vn);
         const float gN = gz_row(r + 2);
 #pragma unroll
         for (int k = 0; k < kHeadCB; ++k) {
@@ -349,9 +353,10 @@ disp_head_gw_kernel(const HeadParams p) {
         gA = gB; gB = gC; gC = gN;
     };
 #pragma unroll 1
-    for (int r = y0 - 1; r <= y1; r += 2) {     // an extra step past y1 only meets gz = 0
-        step(r, va, vb);
+    for (int r = y0 - 1; r <= y1; r += 3) {     // steps past y1 only meet gz = 0
+        step(r, va, vc);
         step(r + 1, vb, va);
+        step(r + 2, vc, vb);
     }
     const int per = p.n_chunks * p.n_strips;
     const int j = chunk * p.n_strips + strip;
