@@ -174,10 +174,11 @@ disp_head_bwd_kernel(const HeadParams p) {
 // ---------------------------------------------------------------------------------------------------------------
 // Tile kernels for the large heads (scales 0 and 1: few channels, many pixels).  The warp march above keeps one row of
 // loads in flight per warp, which leaves the two big heads latency-bound at < 1 TB/s; here every thread owns a column
-// of six output rows, addresses its 8 x 3 neighbourhood directly (L1 serves the horizontal and vertical overlap), and
-// has all 24 loads of a channel in flight at once.  Block = 32 x 8 threads = a 32 x 48 pixel tile (forward).
+// of four output rows, addresses its 6 x 3 neighbourhood directly (L1 serves the horizontal and vertical overlap), and
+// has the 18 loads of a channel (two channels forward) in flight at once.  Block = 32 x 8 threads = a 32 x 32 pixel tile.
+// (Measured, scale 0: 4 rows x 2 channels per thread 53 us; 6 rows x 1 channel at 3 blocks per SM 89 us.)
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kHeadTileRows = 6;    // output rows per thread, forward (a block of 32 x 8 threads covers 32 x 48 pixels)
+constexpr int kHeadTileRows = 4;    // output rows per thread, forward (a block of 32 x 8 threads covers 32 x 32 pixels)
 constexpr int kHeadGxRows = 4;      // ... input-gradient kernel (32 x 32 pixels)
 
 constexpr int kHeadTileH = 8 * kHeadTileRows, kHeadGxTileH = 8 * kHeadGxRows;   // tile heights
@@ -202,7 +203,7 @@ __device__ __forceinline__ HeadTileIdx head_tile_idx(int h, int w) {
 }
 
 // forward: grid = (ceil(w/32), ceil(h/32), B); dynamic smem = C * 12 floats
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256)
 disp_head_fwd_tile_kernel(const HeadParams p) {
     PML_DYN_SMEM(float, sw);
     const int C = p.C, h = p.h, w = p.w, plane = h * w;
@@ -214,8 +215,8 @@ disp_head_fwd_tile_kernel(const HeadParams p) {
     float a[kHeadTileRows];
 #pragma unroll
     for (int i = 0; i < kHeadTileRows; ++i) a[i] = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < C; ++c, xc += plane) {
+#pragma unroll 2
+    for (int c = 0; c < C; ++c, xc += plane) {      // two channels = 36 loads in flight per thread
         float v[kHeadTileRows + 2][3];
 #pragma unroll
         for (int j = 0; j < kHeadTileRows + 2; ++j)
