@@ -329,9 +329,9 @@ def run_ours(args, rank, world, dev):
             last = None
             for i in range(n):
                 cur = nxt
-                if i + 1 < n:
-                    nxt = upload(host[(i + 1) % len(host)])
                 loss = compute(*cur)
+                if i + 1 < n:        # enqueued behind this step's launches, runs beside its kernels
+                    nxt = upload(host[(i + 1) % len(host)])
                 last = loss.item()   # D2H read of the step's result
             return last
 
@@ -414,9 +414,10 @@ def run_ours(args, rank, world, dev):
             last = None
             for i in range(n):
                 cur = nxt
-                if i + 1 < n:
+                loss = compute(i % 2, cur, i)
+                if i + 1 < n:        # enqueued behind this step's launches, runs beside its kernels
                     nxt = upload(host[(i + 1) % len(host)], (i + 1) % 2)
-                last = compute(i % 2, cur, i).item()   # D2H read of the step's result
+                last = loss.item()   # D2H read of the step's result
             return last
 
         Ke = max(3, min(K, 100))
