@@ -139,6 +139,8 @@ struct PyramidPackedParams {
     const uint8_t* parent;   // [N, 2h, 2w, 3]
     uint8_t* child;          // [N, h, w, 3] (nullable for the last level)
     float* child_f;          // [N, 3, h, w]
+    float* parent_f;         // [N, 3, 2h, 2w] or null: ToTensor of the parent written from the staged window (level 1:
+                             // saves the separate pass over the scale-0 frames); needs 16-byte aligned planes
     int N, h, w;
     ResampleLimbs lx, ly;
 };
@@ -208,6 +210,18 @@ pyramid_level_packed_kernel(const PyramidPackedParams q) {
             cr = (a & 255u) | ((a >> 24) << 8) | (((b >> 16) & 255u) << 16) | (((c >> 8) & 255u) << 24);
             cg = ((a >> 8) & 255u) | ((b & 255u) << 8) | ((b >> 24) << 16) | (((c >> 16) & 255u) << 24);
             cb = ((a >> 16) & 255u) | (((b >> 8) & 255u) << 8) | ((c & 255u) << 16) | ((c >> 24) << 24);
+            // the parent pixels under this tile's outputs (every parent pixel belongs to exactly one tile)
+            if (q.parent_f != nullptr && r >= 8 && r < 8 + 2 * kPyrTOH && g >= 2 && g < 2 + kPyrTOW / 2) {
+                float* d = q.parent_f + ((size_t)n * 3 * ph + y) * pw + x;
+                const float k = 255.0f;
+                const size_t pl = (size_t)ph * pw;
+                *reinterpret_cast<float4*>(d) = make_float4(__fdiv_rn((float)(cr & 255u), k), __fdiv_rn((float)((cr >> 8) & 255u), k),
+                                                            __fdiv_rn((float)((cr >> 16) & 255u), k), __fdiv_rn((float)(cr >> 24), k));
+                *reinterpret_cast<float4*>(d + pl) = make_float4(__fdiv_rn((float)(cg & 255u), k), __fdiv_rn((float)((cg >> 8) & 255u), k),
+                                                                 __fdiv_rn((float)((cg >> 16) & 255u), k), __fdiv_rn((float)(cg >> 24), k));
+                *reinterpret_cast<float4*>(d + 2 * pl) = make_float4(__fdiv_rn((float)(cb & 255u), k), __fdiv_rn((float)((cb >> 8) & 255u), k),
+                                                                     __fdiv_rn((float)((cb >> 16) & 255u), k), __fdiv_rn((float)(cb >> 24), k));
+            }
         }
         s_pl[0][r][g] = cr; s_pl[1][r][g] = cg; s_pl[2][r][g] = cb;
     }
