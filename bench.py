@@ -299,7 +299,7 @@ def run_ours(args, rank, world, dev):
             host.append(hostio.PinnedBatch(hb))      # one pinned arena per batch: a single H2D copy per step
         h2d = host[0].nbytes
 
-        # Double-buffered like a DataLoader with pin_memory: the H2D copy of step i+1 runs on a copy
+        # Prefetched like a DataLoader with pin_memory: the H2D copies of the next two steps run on a copy
         # stream while the kernels of step i run on the compute stream.  Every step still uploads its
         # own inputs from pinned host memory and reads its loss back inside the timed region.
         copy_stream = torch.cuda.Stream(device=dev)
@@ -325,13 +325,15 @@ def run_ours(args, rank, world, dev):
             return losses["loss"]
 
         def run_steps(n):
-            nxt = upload(host[0])
+            # uploads run two steps ahead of the kernels (a DataLoader with prefetch_factor 2): with 8 ranks sharing the
+            # host's memory system one 13-67 MB copy takes about as long as a whole step
+            pending = [upload(host[j % len(host)]) for j in range(min(2, n))]
             last = None
             for i in range(n):
-                cur = nxt
+                cur = pending.pop(0)
                 loss = compute(*cur)
-                if i + 1 < n:        # enqueued behind this step's launches, runs beside its kernels
-                    nxt = upload(host[(i + 1) % len(host)])
+                if i + 2 < n:        # enqueued behind this step's launches
+                    pending.append(upload(host[(i + 2) % len(host)]))
                 last = loss.item()   # D2H read of the step's result
             return last
 
@@ -357,7 +359,7 @@ def run_ours(args, rank, world, dev):
     def e2e_graph_arm():
         """The same step through trainer_hooks.GraphedLoss: ingest + fused loss captured once per slot as a CUDA
         graph on static input slots; per step one H2D copy into the slot (copy stream), one graph launch, the
-        eager backward (one kernel) and loss.item().  Two slots: the upload of step i+1 overlaps step i."""
+        eager backward (one kernel) and loss.item().  Three slots: uploads run two steps ahead of the kernels."""
         from ssde_b200 import hostio
         o2 = SimpleNamespace(**vars(opt))
         o2.pml_sources, o2.pml_variant, o2.pml_emit_depth = srcs, "trainer", "scale0"
@@ -378,7 +380,8 @@ def run_ours(args, rank, world, dev):
         copy_stream = torch.cuda.Stream(device=dev)
         main_stream = torch.cuda.current_stream(dev)
         slots = []
-        for s in range(2):
+        NS = 3     # three slots: the upload of step i+2 runs while step i computes and step i+1's inputs are already resident
+        for s in range(NS):
             d, arena = host[0].upload(dev)
             torch.cuda.synchronize()
             inp = dict(d)
@@ -397,27 +400,28 @@ def run_ours(args, rank, world, dev):
                 ev.record(copy_stream)
             return ev
 
-        def compute(s, ev, i):
+        def forward(s, ev, i):
             slot, arena, out, done = slots[s]
             main_stream.wait_event(ev)
             for k in diff_keys:
                 out[k].grad = None
             with torch.no_grad():     # this step's network outputs land in the slot (one multi-tensor copy)
                 torch._foreach_copy_([out[k] for k in diff_keys], [net[i % len(net)][k] for k in diff_keys])
-            losses = slot.replay()
+            return slot.replay()
+
+        def backward(s, losses):
             losses["loss"].backward()
-            done.record(main_stream)
+            slots[s][3].record(main_stream)
             return losses["loss"]
 
         def run_steps(n):
-            nxt = upload(host[0], 0)
+            pending = [upload(host[j % len(host)], j % NS) for j in range(min(2, n))]
             last = None
             for i in range(n):
-                cur = nxt
-                loss = compute(i % 2, cur, i)
-                if i + 1 < n:        # enqueued behind this step's launches, runs beside its kernels
-                    nxt = upload(host[(i + 1) % len(host)], (i + 1) % 2)
-                last = loss.item()   # D2H read of the step's result
+                losses = forward(i % NS, pending.pop(0), i)
+                if i + 2 < n:        # two steps ahead, enqueued behind this step's graph launch
+                    pending.append(upload(host[(i + 2) % len(host)], (i + 2) % NS))
+                last = backward(i % NS, losses).item()   # D2H read of the step's result
             return last
 
         Ke = max(3, min(K, 100))
@@ -436,8 +440,8 @@ def run_ours(args, rank, world, dev):
                 "(network outputs) device-resident, a different set copied into the slot every step",
                 "api": "trainer_hooks.GraphedLoss (opt-in CUDA-graph mode of the drop-in pair generate_images_pred + compute_losses, "
                        "uint8 ingest inside the graph): per step one H2D copy of the pinned host arena (hostio.PinnedBatch) into a "
-                       "static slot on a copy stream, slot.replay(), loss.backward(), loss.item(); two slots, upload of step i+1 "
-                       "overlapped with step i"}
+                       "static slot on a copy stream, slot.replay(), loss.backward(), loss.item(); three slots, uploads run two "
+                       "steps ahead of the kernels"}
 
     e2e_eager = None
     if not args.no_e2e:
