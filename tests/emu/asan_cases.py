@@ -19,6 +19,15 @@ for sources, (B, H, W) in (((-1, 1, -2, 2, "s"), (1, 32, 64)), ((-1, 1, -2, 2, -
     inputs, outputs = synthetic.make_batch(B, H, W, sources=sources, seed=6, scales=opt.scales)
     got = common.run_product(opt, inputs, outputs, "trainer", device="cpu", noise_seed=None, sources=sources)
     print(sources, (B, H, W), "ok", float(got["loss"]))
+# default training configuration (in-kernel noise, no by-product stores): selection pre-pass + COMMON modes 1/3/2, the scalar
+# single-frame instantiation (3 and 5 sources, stereo-only), odd sizes
+for sources, (B, H, W) in (((-1, 1, "s"), (2, 40, 104)), ((-1, 1, -2, 2), (1, 32, 64)), ((-1, 1, -2, 2, "s"), (1, 24, 40)), (("s",), (2, 40, 72)),
+                           ((-1, 1, -2, 2, -3, 3, "s"), (1, 24, 40))):
+    opt = synthetic.make_options(H, W, batch_size=B, scales=[0, 1, 2])
+    inputs, outputs = synthetic.make_batch(B, H, W, sources=sources, seed=7, scales=opt.scales)
+    got = common.run_product(opt, inputs, outputs, "trainer", device="cpu", noise_seed=None, sources=sources,
+                             extra_opt=dict(pml_emit_warped=False, pml_emit_depth="scale0"))
+    print("default configuration", sources, (B, H, W), "ok", float(got["loss"]))
 # pyramid: packed + scalar kernels, border tiles, non-multiple tile sizes
 rng = np.random.default_rng(0)
 for (N, H, W, n) in ((2, 96, 160, 4), (1, 32, 64, 4), (1, 8, 16, 4), (1, 40, 72, 2), (3, 192, 640, 4)):
@@ -26,7 +35,7 @@ for (N, H, W, n) in ((2, 96, 160, 4), (1, 32, 64, 4), (1, 8, 16, 4), (1, 40, 72,
     out = Fn.color_pyramid(fr, n)
     print("pyramid", (N, H, W, n), "ok", float(out[-1].mean()))
 # disparity heads: forward / backward on sizes off the 30-column strips and 16-row chunks, channel split over warps
-for (B, C, h, w) in ((2, 16, 37, 95), (1, 128, 6, 5), (1, 64, 17, 31), (3, 32, 16, 30)):
+for (B, C, h, w) in ((2, 16, 37, 95), (1, 128, 6, 5), (1, 64, 17, 31), (3, 32, 16, 30), (9, 5, 70, 150), (40, 3, 33, 65)):   # the last two: tiled kernels
     x = torch.randn(B, C, h, w, requires_grad=True)
     wt, bs = (torch.randn(1, C, 3, 3) * 0.1).requires_grad_(True), torch.zeros(1, requires_grad=True)
     d = Fn.disp_head(x, wt, bs)
