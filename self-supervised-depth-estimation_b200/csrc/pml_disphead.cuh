@@ -240,6 +240,106 @@ disp_head_fwd_tile_kernel(const HeadParams p) {
     }
 }
 
+// ---- forward, staged: the same 32 x 32 tile, but the 34 x 40 float window of four channels at a time travels to shared
+// memory with 16-byte cp.async copies (no registers held while in flight), double-buffered: one stage loads while the
+// other is consumed, five blocks per SM keep > 100 KB in flight per SM.  Needs w % 4 == 0 and a 16-byte aligned x
+// (the window starts at column x0 - 4 so that every copy is aligned); reflection is an index map on the shared-memory
+// reads -- the reflected row / column of a border tile lies inside its own window.
+constexpr int kHeadStCB = 4, kHeadStRows = 34, kHeadStCols = 40;
+constexpr int kHeadStFloats = kHeadStCB * kHeadStRows * kHeadStCols;     // one stage
+
+__device__ __forceinline__ void head_cp_async16(float* smem_dst, const float* gsrc) {
+#ifdef PML_HOST_EMU
+    for (int i = 0; i < 4; ++i) smem_dst[i] = gsrc[i];
+#else
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+#endif
+}
+__device__ __forceinline__ void head_cp_async_commit() {
+#ifndef PML_HOST_EMU
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+__device__ __forceinline__ void head_cp_async_wait() {
+#ifndef PML_HOST_EMU
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+
+// grid = (ceil(w/32), ceil(h/32), B); dynamic smem = (2 stages + C * 12 weights) floats
+__global__ void __launch_bounds__(256)
+disp_head_fwd_staged_kernel(const HeadParams p) {
+    PML_DYN_SMEM(float, sm);
+    const int C = p.C, h = p.h, w = p.w, plane = h * w;
+    float* sw = sm + 2 * kHeadStFloats;
+    for (int i = threadIdx.x; i < C * 9; i += blockDim.x) sw[(i / 9) * 12 + (i % 9)] = p.weight[i];
+    const int b = blockIdx.z;
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const float* xb = p.x + (size_t)b * C * plane;
+    const int wx0 = x0 - 4, wy0 = y0 - 1;                 // window origin
+    auto issue = [&](int c0, float* stage) {              // channels c0 .. c0+3 (those < C)
+        for (int t = threadIdx.x; t < kHeadStCB * kHeadStRows * (kHeadStCols / 4); t += 256) {
+            const int g = t % (kHeadStCols / 4), rr = (t / (kHeadStCols / 4)) % kHeadStRows, k = t / ((kHeadStCols / 4) * kHeadStRows);
+            const int y = wy0 + rr, x = wx0 + 4 * g;
+            if (c0 + k < C && y >= 0 && y < h && x >= 0 && x < w)        // w % 4 == 0: a group is inside or outside as a whole
+                head_cp_async16(stage + (k * kHeadStRows + rr) * kHeadStCols + 4 * g, xb + (size_t)(c0 + k) * plane + y * w + x);
+        }
+        head_cp_async_commit();
+    };
+    // shared-memory coordinates of the 6 x 3 neighbourhood of this thread's four outputs (rows y0 + 4 ty .. + 3)
+    const int cx = x0 + tx, q0 = y0 + 4 * ty;
+    const int cxc = min(cx, w - 1);
+    int co[3], ro[6];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) co[k] = reflect1(cxc + k - 1, w) - wx0;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) ro[j] = (reflect1(min(q0 - 1 + j, h), h) - wy0) * kHeadStCols;
+    // rows past the image (q0 - 1 + j > h) map to row h-2 of the image, which may lie above this tile's window only
+    // when the whole thread is outside the image; clamp keeps the (unused) reads inside the stage
+#pragma unroll
+    for (int j = 0; j < 6; ++j) ro[j] = min(max(ro[j], 0), (kHeadStRows - 1) * kHeadStCols);
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    const int n_st = (C + kHeadStCB - 1) / kHeadStCB;
+    issue(0, sm);
+    for (int st = 0; st < n_st; ++st) {
+        float* cur = sm + (st & 1) * kHeadStFloats;
+        if (st + 1 < n_st) { issue((st + 1) * kHeadStCB, sm + ((st + 1) & 1) * kHeadStFloats); head_cp_async_wait<1>(); }
+        else head_cp_async_wait<0>();
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kHeadStCB; ++k) {
+            const int c = st * kHeadStCB + k;
+            if (c < C) {
+                const float* sc = cur + k * kHeadStRows * kHeadStCols;
+                float v[6][3];
+#pragma unroll
+                for (int j = 0; j < 6; ++j)
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) v[j][d] = sc[ro[j] + co[d]];
+                const float4* wk = reinterpret_cast<const float4*>(sw + c * 12);
+                const float4 w0 = wk[0], w1 = wk[1], w2 = wk[2];
+                const float W[9] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) a[i] = fmaf(W[dy * 3 + d], v[i + dy][d], a[i]);
+            }
+        }
+        __syncthreads();     // the stage is free for the copy issued in the next iteration
+    }
+    const float bias = __ldg(p.bias);
+    if (cx < w) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (q0 + i < h) p.disp[(size_t)b * plane + (q0 + i) * w + cx] = sigmoidf(a[i] + bias);
+    }
+}
+
 // backward, input gradient: same tiling.  The folded gz neighbourhood of the four output rows (see the comment of
 // disp_head_bwd_kernel) is computed once per thread and serves every channel: nine FMAs and one store per channel.
 __global__ void __launch_bounds__(256)

@@ -35,7 +35,7 @@ for (N, H, W, n) in ((2, 96, 160, 4), (1, 32, 64, 4), (1, 8, 16, 4), (1, 40, 72,
     out = Fn.color_pyramid(fr, n)
     print("pyramid", (N, H, W, n), "ok", float(out[-1].mean()))
 # disparity heads: forward / backward on sizes off the 30-column strips and 16-row chunks, channel split over warps
-for (B, C, h, w) in ((2, 16, 37, 95), (1, 128, 6, 5), (1, 64, 17, 31), (3, 32, 16, 30), (9, 5, 70, 150), (40, 3, 33, 65)):   # the last two: tiled kernels
+for (B, C, h, w) in ((2, 16, 37, 95), (1, 128, 6, 5), (1, 64, 17, 31), (3, 32, 16, 30), (9, 5, 70, 150), (40, 3, 33, 65), (40, 6, 33, 68)):   # the last three: tiled kernels (register tile, staged)
     x = torch.randn(B, C, h, w, requires_grad=True)
     wt, bs = (torch.randn(1, C, 3, 3) * 0.1).requires_grad_(True), torch.zeros(1, requires_grad=True)
     d = Fn.disp_head(x, wt, bs)

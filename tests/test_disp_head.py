@@ -51,19 +51,21 @@ def _check_kernels(device):
 
     # enough 32 x 32 tiles for the tiled kernels of the large heads (pml_head_tiled: B * tiles >= 296), sizes that
     # are not multiples of the tile, a channel count that is not a multiple of the 8-channel march; with and without g_x
-    x = torch.randn(9, 5, 70, 150, generator=g)
-    w, b = torch.randn(1, 5, 3, 3, generator=g) * 0.2, torch.randn(1, generator=g)
-    gd = torch.randn(9, 1, 70, 150, generator=g)
-    ref = dho.run(x, w, b, gd)
-    for with_gx in (True, False):
-        xd = x.clone().to(device).requires_grad_(with_gx)
-        wd, bd = w.clone().to(device).requires_grad_(True), b.clone().to(device).requires_grad_(True)
-        disp = Fn.disp_head(xd, wd, bd)
-        disp.backward(gd.to(device))
-        assert (disp.detach().double().cpu() - ref["disp"]).abs().max() < 2e-6
-        assert common.rel_err(wd.grad.cpu(), ref["g_weight"]) < 2e-5 and common.rel_err(bd.grad.cpu(), ref["g_bias"]) < 2e-5
-        if with_gx:
-            assert common.rel_err(xd.grad.cpu(), ref["g_x"]) < 2e-5
+    # (9, 5, 70, 150): register-tile forward (w % 4 != 0); (20, 6, 70, 152): forward staged through shared memory (cp.async)
+    for (Bt, Ct, ht, wt_) in ((9, 5, 70, 150), (20, 6, 70, 152)):
+        x = torch.randn(Bt, Ct, ht, wt_, generator=g)
+        w, b = torch.randn(1, Ct, 3, 3, generator=g) * 0.2, torch.randn(1, generator=g)
+        gd = torch.randn(Bt, 1, ht, wt_, generator=g)
+        ref = dho.run(x, w, b, gd)
+        for with_gx in (True, False):
+            xd = x.clone().to(device).requires_grad_(with_gx)
+            wd, bd = w.clone().to(device).requires_grad_(True), b.clone().to(device).requires_grad_(True)
+            disp = Fn.disp_head(xd, wd, bd)
+            disp.backward(gd.to(device))
+            assert (disp.detach().double().cpu() - ref["disp"]).abs().max() < 2e-6
+            assert common.rel_err(wd.grad.cpu(), ref["g_weight"]) < 2e-5 and common.rel_err(bd.grad.cpu(), ref["g_bias"]) < 2e-5
+            if with_gx:
+                assert common.rel_err(xd.grad.cpu(), ref["g_x"]) < 2e-5
 
 
 def test_kernels_on_the_emulator(emu_lib):
