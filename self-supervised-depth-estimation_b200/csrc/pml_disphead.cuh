@@ -240,12 +240,15 @@ disp_head_fwd_tile_kernel(const HeadParams p) {
     }
 }
 
-// ---- forward, staged: the same 32 x 32 tile, but the 34 x 40 float window of four channels at a time travels to shared
-// memory with 16-byte cp.async copies (no registers held while in flight), double-buffered: one stage loads while the
-// other is consumed, five blocks per SM keep > 100 KB in flight per SM.  Needs w % 4 == 0 and a 16-byte aligned x
-// (the window starts at column x0 - 4 so that every copy is aligned); reflection is an index map on the shared-memory
-// reads -- the reflected row / column of a border tile lies inside its own window.
-constexpr int kHeadStCB = 4, kHeadStRows = 34, kHeadStCols = 40;
+// ---- forward, staged: a 128 x 8 pixel tile per block (long row segments: a 32-column tile reads 128-160 bytes per DRAM
+// page it opens and stalls at 2 TB/s however much is in flight -- measured with this very kernel at 32 x 32: 47 us);
+// the 10 x 136 float window of four channels at a time travels to shared memory with 16-byte cp.async copies (no
+// registers held while in flight), double-buffered: one stage loads while the other is consumed, five blocks per SM keep
+// > 100 KB in flight per SM.  Needs w % 4 == 0 and a 16-byte aligned x (the window starts at column x0 - 4 so that every
+// copy is aligned); reflection is an index map on the shared-memory reads -- the reflected row / column of a border
+// tile lies inside its own window.
+constexpr int kHeadStW = 128, kHeadStH = 8;      // tile; 256 threads = 128 columns x 2 groups of 4 rows
+constexpr int kHeadStCB = 4, kHeadStRows = kHeadStH + 2, kHeadStCols = kHeadStW + 8;
 constexpr int kHeadStFloats = kHeadStCB * kHeadStRows * kHeadStCols;     // one stage
 
 __device__ __forceinline__ void head_cp_async16(float* smem_dst, const float* gsrc) {
@@ -268,7 +271,7 @@ __device__ __forceinline__ void head_cp_async_wait() {
 #endif
 }
 
-// grid = (ceil(w/32), ceil(h/32), B); dynamic smem = (2 stages + C * 12 weights) floats
+// grid = (ceil(w/128), ceil(h/8), B); dynamic smem = (2 stages + C * 12 weights) floats
 __global__ void __launch_bounds__(256)
 disp_head_fwd_staged_kernel(const HeadParams p) {
     PML_DYN_SMEM(float, sm);
@@ -276,8 +279,8 @@ disp_head_fwd_staged_kernel(const HeadParams p) {
     float* sw = sm + 2 * kHeadStFloats;
     for (int i = threadIdx.x; i < C * 9; i += blockDim.x) sw[(i / 9) * 12 + (i % 9)] = p.weight[i];
     const int b = blockIdx.z;
-    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int x0 = blockIdx.x * kHeadStW, y0 = blockIdx.y * kHeadStH;
+    const int tx = threadIdx.x & (kHeadStW - 1), ty = threadIdx.x / kHeadStW;
     const float* xb = p.x + (size_t)b * C * plane;
     const int wx0 = x0 - 4, wy0 = y0 - 1;                 // window origin
     auto issue = [&](int c0, float* stage) {              // channels c0 .. c0+3 (those < C)
@@ -290,6 +293,7 @@ disp_head_fwd_staged_kernel(const HeadParams p) {
         head_cp_async_commit();
     };
     // shared-memory coordinates of the 6 x 3 neighbourhood of this thread's four outputs (rows y0 + 4 ty .. + 3)
+    static_assert(kHeadStW * (kHeadStH / 4) == 256, "one thread per column and group of four rows");
     const int cx = x0 + tx, q0 = y0 + 4 * ty;
     const int cxc = min(cx, w - 1);
     int co[3], ro[6];
