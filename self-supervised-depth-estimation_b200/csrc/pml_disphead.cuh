@@ -247,7 +247,7 @@ disp_head_fwd_tile_kernel(const HeadParams p) {
 // > 100 KB in flight per SM.  Needs w % 4 == 0 and a 16-byte aligned x (the window starts at column x0 - 4 so that every
 // copy is aligned); reflection is an index map on the shared-memory reads -- the reflected row / column of a border
 // tile lies inside its own window.
-constexpr int kHeadStW = 128, kHeadStH = 8;      // tile; 256 threads = 128 columns x 2 groups of 4 rows
+constexpr int kHeadStW = 128, kHeadStH = 8;      // tile; 128 threads = 32 groups of 4 columns x 4 groups of 2 rows
 constexpr int kHeadStCB = 4, kHeadStRows = kHeadStH + 2, kHeadStCols = kHeadStW + 8;
 constexpr int kHeadStFloats = kHeadStCB * kHeadStRows * kHeadStCols;     // one stage
 
@@ -271,8 +271,11 @@ __device__ __forceinline__ void head_cp_async_wait() {
 #endif
 }
 
-// grid = (ceil(w/128), ceil(h/8), B); dynamic smem = (2 stages + C * 12 weights) floats
-__global__ void __launch_bounds__(256)
+// grid = (ceil(w/128), ceil(h/8), B), 128 threads; dynamic smem = (2 stages + C * 12 weights) floats.
+// A thread owns 4 columns x 2 rows: per channel 4 input rows x (one 128-bit + two 32-bit shared-memory loads), 72 FMAs and
+// two 128-bit stores at the end -- the first version (one column x four rows per thread, 18 scalar loads per channel, a
+// div/mod per staged chunk) was issue-bound at 84 % issue / 47 us.
+__global__ void __launch_bounds__(128)
 disp_head_fwd_staged_kernel(const HeadParams p) {
     PML_DYN_SMEM(float, sm);
     const int C = p.C, h = p.h, w = p.w, plane = h * w;
@@ -280,32 +283,45 @@ disp_head_fwd_staged_kernel(const HeadParams p) {
     for (int i = threadIdx.x; i < C * 9; i += blockDim.x) sw[(i / 9) * 12 + (i % 9)] = p.weight[i];
     const int b = blockIdx.z;
     const int x0 = blockIdx.x * kHeadStW, y0 = blockIdx.y * kHeadStH;
-    const int tx = threadIdx.x & (kHeadStW - 1), ty = threadIdx.x / kHeadStW;
     const float* xb = p.x + (size_t)b * C * plane;
     const int wx0 = x0 - 4, wy0 = y0 - 1;                 // window origin
+    // the 10 x 34 sixteen-byte chunks of one channel's window: this thread copies chunks t, t + 128, t + 256 of every channel
+    constexpr int kChunks = kHeadStRows * (kHeadStCols / 4);
+    int s_off[3], g_off[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int t = threadIdx.x + 128 * i;
+        const int rr = t / (kHeadStCols / 4), g = t - rr * (kHeadStCols / 4);
+        const int y = wy0 + rr, x = wx0 + 4 * g;
+        const bool ok = t < kChunks && y >= 0 && y < h && x >= 0 && x < w;    // w % 4 == 0: a chunk is inside or outside as a whole
+        s_off[i] = ok ? rr * kHeadStCols + 4 * g : -1;
+        g_off[i] = y * w + x;
+    }
     auto issue = [&](int c0, float* stage) {              // channels c0 .. c0+3 (those < C)
-        for (int t = threadIdx.x; t < kHeadStCB * kHeadStRows * (kHeadStCols / 4); t += 256) {
-            const int g = t % (kHeadStCols / 4), rr = (t / (kHeadStCols / 4)) % kHeadStRows, k = t / ((kHeadStCols / 4) * kHeadStRows);
-            const int y = wy0 + rr, x = wx0 + 4 * g;
-            if (c0 + k < C && y >= 0 && y < h && x >= 0 && x < w)        // w % 4 == 0: a group is inside or outside as a whole
-                head_cp_async16(stage + (k * kHeadStRows + rr) * kHeadStCols + 4 * g, xb + (size_t)(c0 + k) * plane + y * w + x);
+#pragma unroll
+        for (int k = 0; k < kHeadStCB; ++k) {
+            if (c0 + k < C) {
+                const float* gc = xb + (size_t)(c0 + k) * plane;
+                float* sc = stage + k * kHeadStRows * kHeadStCols;
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                    if (s_off[i] >= 0) head_cp_async16(sc + s_off[i], gc + g_off[i]);
+            }
         }
         head_cp_async_commit();
     };
-    // shared-memory coordinates of the 6 x 3 neighbourhood of this thread's four outputs (rows y0 + 4 ty .. + 3)
-    static_assert(kHeadStW * (kHeadStH / 4) == 256, "one thread per column and group of four rows");
-    const int cx = x0 + tx, q0 = y0 + 4 * ty;
-    const int cxc = min(cx, w - 1);
-    int co[3], ro[6];
+    const int cg = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const int cx = x0 + 4 * cg, q0 = y0 + 2 * rg;         // first column / row of this thread's 4 x 2 outputs
+    const int iv = 4 * cg + 4;                            // window column of cx (16-byte aligned)
+    const int il = reflect1(min(cx, w) - 1, w) - wx0, ir = max(reflect1(min(cx + 4, w), w) - wx0, 0);
+    int ro[4];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) co[k] = reflect1(cxc + k - 1, w) - wx0;
+    for (int j = 0; j < 4; ++j) ro[j] = min(max(reflect1(min(q0 - 1 + j, h), h) - wy0, 0), kHeadStRows - 1) * kHeadStCols;
+    float a[2][4];
 #pragma unroll
-    for (int j = 0; j < 6; ++j) ro[j] = (reflect1(min(q0 - 1 + j, h), h) - wy0) * kHeadStCols;
-    // rows past the image (q0 - 1 + j > h) map to row h-2 of the image, which may lie above this tile's window only
-    // when the whole thread is outside the image; clamp keeps the (unused) reads inside the stage
+    for (int r = 0; r < 2; ++r)
 #pragma unroll
-    for (int j = 0; j < 6; ++j) ro[j] = min(max(ro[j], 0), (kHeadStRows - 1) * kHeadStCols);
-    float a[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int j = 0; j < 4; ++j) a[r][j] = 0.f;
     const int n_st = (C + kHeadStCB - 1) / kHeadStCB;
     issue(0, sm);
     for (int st = 0; st < n_st; ++st) {
@@ -318,20 +334,23 @@ disp_head_fwd_staged_kernel(const HeadParams p) {
             const int c = st * kHeadStCB + k;
             if (c < C) {
                 const float* sc = cur + k * kHeadStRows * kHeadStCols;
-                float v[6][3];
+                float v[4][6];
 #pragma unroll
-                for (int j = 0; j < 6; ++j)
-#pragma unroll
-                    for (int d = 0; d < 3; ++d) v[j][d] = sc[ro[j] + co[d]];
+                for (int j = 0; j < 4; ++j) {
+                    const float4 m = *reinterpret_cast<const float4*>(sc + ro[j] + iv);
+                    v[j][0] = sc[ro[j] + il]; v[j][1] = m.x; v[j][2] = m.y; v[j][3] = m.z; v[j][4] = m.w; v[j][5] = sc[ro[j] + ir];
+                }
                 const float4* wk = reinterpret_cast<const float4*>(sw + c * 12);
                 const float4 w0 = wk[0], w1 = wk[1], w2 = wk[2];
                 const float W[9] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x};
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                for (int r = 0; r < 2; ++r)
 #pragma unroll
-                    for (int dy = 0; dy < 3; ++dy)
+                    for (int j = 0; j < 4; ++j)
 #pragma unroll
-                        for (int d = 0; d < 3; ++d) a[i] = fmaf(W[dy * 3 + d], v[i + dy][d], a[i]);
+                        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                            for (int d = 0; d < 3; ++d) a[r][j] = fmaf(W[dy * 3 + d], v[r + dy][j + d], a[r][j]);
             }
         }
         __syncthreads();     // the stage is free for the copy issued in the next iteration
@@ -339,8 +358,10 @@ disp_head_fwd_staged_kernel(const HeadParams p) {
     const float bias = __ldg(p.bias);
     if (cx < w) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            if (q0 + i < h) p.disp[(size_t)b * plane + (q0 + i) * w + cx] = sigmoidf(a[i] + bias);
+        for (int r = 0; r < 2; ++r)
+            if (q0 + r < h)
+                *reinterpret_cast<float4*>(p.disp + (size_t)b * plane + (q0 + r) * w + cx) =
+                    make_float4(sigmoidf(a[r][0] + bias), sigmoidf(a[r][1] + bias), sigmoidf(a[r][2] + bias), sigmoidf(a[r][3] + bias));
     }
 }
 
