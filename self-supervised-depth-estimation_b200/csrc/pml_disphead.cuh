@@ -502,6 +502,131 @@ disp_head_gw_kernel(const HeadParams p) {
     }
 }
 
+// ---- backward, weight / bias gradient, staged like the forward: a block owns four channels of a 128-column stripe over
+// 32 rows (four 128 x 8 tiles, double-buffered through shared memory), a thread the same 4 x 2 window positions in every
+// tile: gz from two 128-bit loads per row, per channel 4 x (one 128-bit + two 32-bit) shared-memory loads and 72 FMAs into
+// the nine accumulators of that channel; one block reduction at the end.  part layout as above with
+// per = stripes x row groups (the launcher passes them in n_strips / n_chunks for disp_head_reduce_kernel).
+constexpr int kHeadGwTiles = 4;      // tiles (of kHeadStH rows) per block
+__global__ void __launch_bounds__(128)
+disp_head_gw_staged_kernel(const HeadParams p) {
+    PML_DYN_SMEM(float, sm);
+    __shared__ float s_red[4][37];
+    const int C = p.C, h = p.h, w = p.w, plane = h * w;
+    const int n_cg = (C + kHeadStCB - 1) / kHeadStCB;
+    const int sx = blockIdx.x, gy = blockIdx.y;
+    const int cgp = blockIdx.z % n_cg, b = blockIdx.z / n_cg;
+    const int c0 = cgp * kHeadStCB;
+    const int x0 = sx * kHeadStW, wx0 = x0 - 4;
+    const float* xb = p.x + ((size_t)b * C + c0) * plane;
+    constexpr int kChunks = kHeadStRows * (kHeadStCols / 4);
+    int s_off[3], g_col[3], g_row[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int t = threadIdx.x + 128 * i;
+        const int rr = t / (kHeadStCols / 4), g = t - rr * (kHeadStCols / 4);
+        const int x = wx0 + 4 * g;
+        s_off[i] = (t < kChunks && x >= 0 && x < w) ? rr * kHeadStCols + 4 * g : -1;
+        g_col[i] = x; g_row[i] = rr;
+    }
+    auto issue = [&](int y0, float* stage) {              // window rows y0-1 .. y0+8 of the four channels
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int y = y0 - 1 + g_row[i];
+            if (s_off[i] >= 0 && y >= 0 && y < h) {
+#pragma unroll
+                for (int k = 0; k < kHeadStCB; ++k)
+                    if (c0 + k < C) head_cp_async16(stage + k * kHeadStRows * kHeadStCols + s_off[i], xb + (size_t)k * plane + y * w + g_col[i]);
+            }
+        }
+        head_cp_async_commit();
+    };
+    const int cg = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const int cx = x0 + 4 * cg;
+    const int iv = 4 * cg + 4;
+    const int il = reflect1(min(cx, w) - 1, w) - wx0, ir = max(reflect1(min(cx + 4, w), w) - wx0, 0);
+    float acc[kHeadStCB][9];
+#pragma unroll
+    for (int k = 0; k < kHeadStCB; ++k)
+#pragma unroll
+        for (int d = 0; d < 9; ++d) acc[k][d] = 0.f;
+    float accb = 0.f;
+    const int yb = gy * (kHeadGwTiles * kHeadStH);
+    const float* gd = p.g_disp + (size_t)b * plane;
+    const float* dd = p.disp + (size_t)b * plane;
+    issue(yb, sm);
+    for (int st = 0; st < kHeadGwTiles; ++st) {
+        const int y0 = yb + st * kHeadStH, wy0 = y0 - 1;
+        float* cur = sm + (st & 1) * kHeadStFloats;
+        if (st + 1 < kHeadGwTiles) { issue(y0 + kHeadStH, sm + ((st + 1) & 1) * kHeadStFloats); head_cp_async_wait<1>(); }
+        else head_cp_async_wait<0>();
+        // gz of this thread's 4 x 2 window positions (0 outside the image)
+        const int q0 = y0 + 2 * rg;
+        float gz[2][4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f), d4 = g4;
+            if (cx < w && q0 + r < h) {
+                g4 = __ldg(reinterpret_cast<const float4*>(gd + (q0 + r) * w + cx));
+                d4 = __ldg(reinterpret_cast<const float4*>(dd + (q0 + r) * w + cx));
+            }
+            gz[r][0] = g4.x * d4.x * (1.f - d4.x); gz[r][1] = g4.y * d4.y * (1.f - d4.y);
+            gz[r][2] = g4.z * d4.z * (1.f - d4.z); gz[r][3] = g4.w * d4.w * (1.f - d4.w);
+            accb += (gz[r][0] + gz[r][1]) + (gz[r][2] + gz[r][3]);
+        }
+        int ro[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ro[j] = min(max(reflect1(min(q0 - 1 + j, h), h) - wy0, 0), kHeadStRows - 1) * kHeadStCols;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kHeadStCB; ++k) {
+            const float* sc = cur + k * kHeadStRows * kHeadStCols;
+            float v[4][6];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 m = *reinterpret_cast<const float4*>(sc + ro[j] + iv);
+                v[j][0] = sc[ro[j] + il]; v[j][1] = m.x; v[j][2] = m.y; v[j][3] = m.z; v[j][4] = m.w; v[j][5] = sc[ro[j] + ir];
+            }
+            // positions outside the image are skipped, not multiplied by gz = 0: their taps may lie in window cells
+            // no copy has written (0 * stale shared memory)
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+                if (cx < w && q0 + r < h) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                            for (int d = 0; d < 3; ++d) acc[k][dy * 3 + d] = fmaf(gz[r][j], v[r + dy][j + d], acc[k][dy * 3 + d]);
+                }
+        }
+        __syncthreads();
+    }
+    // block reduction in a fixed order: lanes by shuffles, then the four warps
+#pragma unroll
+    for (int k = 0; k < kHeadStCB; ++k)
+#pragma unroll
+        for (int d = 0; d < 9; ++d) {
+            const float v = warp_sum(acc[k][d]);
+            if (cg == 0) s_red[rg][k * 9 + d] = v;
+        }
+    {
+        const float v = warp_sum(accb);
+        if (cg == 0) s_red[rg][36] = v;
+    }
+    __syncthreads();
+    const int per = gridDim.x * gridDim.y, j = gy * gridDim.x + sx;
+    if (threadIdx.x < 37) {
+        const float v = (s_red[0][threadIdx.x] + s_red[1][threadIdx.x]) + (s_red[2][threadIdx.x] + s_red[3][threadIdx.x]);
+        if (threadIdx.x < 36) {
+            const int k = threadIdx.x / 9, d = threadIdx.x - 9 * k;
+            if (c0 + k < C) p.part[((size_t)(b * C + c0 + k) * per + j) * 10 + d] = v;
+        } else if (cgp == 0) {
+            p.part[((size_t)(b * C) * per + j) * 10 + 9] = v;
+        }
+    }
+}
+
 // fixed-order reduction of the partials: block c sums the 9 weight gradients of channel c over (image, chunk,
 // strip); block C sums the bias gradient (taken from the items of channel 0).  256 threads.
 __global__ void __launch_bounds__(256)
