@@ -627,33 +627,30 @@ disp_head_gw_staged_kernel(const HeadParams p) {
     }
 }
 
-// fixed-order reduction of the partials: block c sums the 9 weight gradients of channel c over (image, chunk,
-// strip); block C sums the bias gradient (taken from the items of channel 0).  256 threads.
-__global__ void __launch_bounds__(256)
+// fixed-order reduction of the partials: block c sums the 9 weight gradients of channel c over (image, chunk, strip),
+// one warp per tap (lanes stride over the items, lane 0 adds the 32 partial sums in lane order: the order is fixed); block C sums the bias
+// gradient (taken from the items of channel 0).  288 threads.
+__global__ void __launch_bounds__(288)
 disp_head_reduce_kernel(const HeadParams p, float* __restrict__ g_weight, float* __restrict__ g_bias) {
-    __shared__ double s_acc[256];
-    const int c = blockIdx.x;
+    __shared__ double s_acc[9][32];
+    const int c = blockIdx.x, k = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int per = p.n_chunks * p.n_strips;
-    const int ch = (c == p.C) ? 0 : c;
-    const int n_out = (c == p.C) ? 1 : 9;
-    for (int k = 0; k < n_out; ++k) {
-        const int col = (c == p.C) ? 9 : k;
-        double a = 0.0;
-        for (int i = threadIdx.x; i < p.B * per; i += 256) {
+    const bool bias = (c == p.C);
+    const int ch = bias ? 0 : c, col = bias ? 9 : k;
+    double a = 0.0;
+    if (!bias || k == 0) {
+        for (int i = lane; i < p.B * per; i += 32) {
             const int b = i / per, j = i - b * per;
             a += (double)p.part[((size_t)(b * p.C + ch) * per + j) * 10 + col];
         }
-        s_acc[threadIdx.x] = a;
-        __syncthreads();
-        for (int m = 128; m > 0; m >>= 1) {
-            if ((int)threadIdx.x < m) s_acc[threadIdx.x] += s_acc[threadIdx.x + m];
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) {
-            if (c == p.C) g_bias[0] = (float)s_acc[0];
-            else g_weight[c * 9 + k] = (float)s_acc[0];
-        }
-        __syncthreads();
+    }
+    s_acc[k][lane] = a;
+    __syncthreads();
+    if (lane == 0 && (!bias || k == 0)) {
+        double t = 0.0;
+        for (int m = 0; m < 32; ++m) t += s_acc[k][m];
+        if (bias) g_bias[0] = (float)t;
+        else g_weight[c * 9 + k] = (float)t;
     }
 }
 
