@@ -639,9 +639,17 @@ disp_head_reduce_kernel(const HeadParams p, float* __restrict__ g_weight, float*
     const int ch = bias ? 0 : c, col = bias ? 9 : k;
     double a = 0.0;
     if (!bias || k == 0) {
-        for (int i = lane; i < p.B * per; i += 32) {
-            const int b = i / per, j = i - b * per;
-            a += (double)p.part[((size_t)(b * p.C + ch) * per + j) * 10 + col];
+        const int n = p.B * per;
+        for (int i0 = lane; i0 < n; i0 += 32 * 8) {      // eight independent loads in flight per lane, added in index order
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + 32 * u;
+                const int b = i / per, j = i - b * per;
+                v[u] = (i < n) ? p.part[((size_t)(b * p.C + ch) * per + j) * 10 + col] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a += (double)v[u];
         }
     }
     s_acc[k][lane] = a;
