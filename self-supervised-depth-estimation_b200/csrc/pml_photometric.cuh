@@ -643,6 +643,7 @@ finalize_image_kernel(const FinalizeParams q) {
         float v = 0.f;
         if (col < ncol) {
             const float* base = q.part + (size_t)(pi * q.cta_per_pass + b * q.cta_per_image) * q.part_stride + col;
+#pragma unroll 4      // the loads are independent of the running sum: four in flight, added in the same order
             for (int c = seg; c < q.cta_per_image; c += nseg) v += base[(size_t)c * q.part_stride];
         }
         s_seg[tid] = v;
