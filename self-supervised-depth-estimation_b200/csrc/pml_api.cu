@@ -47,12 +47,11 @@ inline void pml_event_record(void* ev, cudaStream_t st) {
 
 // Developer knobs (A/B experiments on the GPU box).  Read ONCE per process, never on the per-call path.
 struct Knobs {
-    int th, id_th, smem_pad, pyramid_scalar, colocate;
+    int th, id_th, smem_pad, pyramid_scalar;
     Knobs() {
         auto geti = [](const char* name, int dflt) { const char* s = getenv(name); return (s && *s) ? atoi(s) : dflt; };
         th = geti("PML_TH", 0); id_th = geti("PML_ID_TH", 16); smem_pad = geti("PML_SMEM_PAD", 0);
         pyramid_scalar = geti("PML_PYRAMID_SCALAR", 0);
-        colocate = geti("PML_COLOCATE", 0);
     }
 };
 const Knobs& knobs() { static const Knobs k; return k; }
@@ -301,11 +300,7 @@ int launch_sweep(const PhotoParams& pp, cudaStream_t st) {
     const bool lone = (pp.mode == 3 || pp.mode == 0) && pp.pair_n == 1;
     const size_t smem = sweep_smem_bytes(GRAD && pp.mode != 1, !lone) + (size_t)(GRAD ? knobs().smem_pad : 0);   // < 48 KB: no opt-in needed
     if (pp.B > 65535) return PML_ERR_UNSUPPORTED;
-    dim3 grid(pp.n_chunks * pp.n_strips, pp.B, pp.n_pass);
-    if (pp.colocate > 0) {
-        const int per_pass = pp.n_chunks * pp.n_strips * pp.B;
-        grid = dim3((unsigned)(pp.colocate * pp.n_pass * ((per_pass + pp.colocate - 1) / pp.colocate)));
-    }
+    const dim3 grid(pp.n_chunks * pp.n_strips, pp.B, pp.n_pass);
     bool emit = false;   // by-products requested by any pass (never in sweep mode 2)
     for (int i = 0; i < pp.n_pass; ++i) emit = emit || pp.pass[i].depth != nullptr || pp.pass[i].warped != nullptr;
     const dim3 blk(kSweepWarps * 32);
@@ -457,7 +452,7 @@ int run_loss(const pml_problem* p, void* ws, size_t ws_bytes, cudaStream_t st, b
     }
     pp.TW = pl.TW; pp.TH = pl.TH; pp.n_strips = pl.n_strips; pp.n_chunks = pl.n_chunks;
     pp.n_items = pl.n_cta; pp.S = p->S;
-    pp.mode = 0; pp.f_base = 0; pp.pair_n = p->S > 1 ? 2 : 1; pp.rp = nullptr; pp.presel = nullptr; pp.colocate = knobs().colocate;
+    pp.mode = 0; pp.f_base = 0; pp.pair_n = p->S > 1 ? 2 : 1; pp.rp = nullptr; pp.presel = nullptr;
     pp.cta_per_pass = pl.cta_per_pass; pp.part = part; pp.part_stride = pl.part_stride;
     pp.inv_n = (float)(1.0 / ((double)p->B * p->H * p->W));
     pp.n_seg = sp.n_seg; pp.seg_size = sp.seg_size;

@@ -55,7 +55,6 @@ struct PhotoParams {
     int f_base;       // first frame of the pair handled by this launch
     int pair_n;       // frames in the pair: 1 or 2
     float* rp;        // [n_pass][S][B][H][W] reprojection losses (written in mode 1, read in mode 3)
-    int colocate;     // > 0: 1-D grid of the sweep, passes of one item `colocate` block ids apart (pml_sweep.cuh)
     uint8_t* presel;  // [n_pass][B][H][W] select_prepass_kernel: best candidate ahead of the last pair (its value: rp slot f_base)
     float* part;      // [n_cta][part_stride]: loss partial, then S x 12 dL/dP partials
     int part_stride;

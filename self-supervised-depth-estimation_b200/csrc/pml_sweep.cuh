@@ -201,22 +201,10 @@ sweep_kernel(const PhotoParams p) {
     // grid = (n_chunks * n_strips, B, n_pass): image and pass come straight from blockIdx, so every
     // base pointer derived from them is warp-uniform by construction (no division on that path)
     const int lane = threadIdx.x;
-    int b = blockIdx.y, pass_i = blockIdx.z, bx = blockIdx.x;
-    if (p.colocate > 0) {
-        // 1-D grid, the passes (scales) of one (image, strip, chunk) item p.colocate block ids apart: on a GPU that hands
-        // out the first wave of blocks round-robin they land on the same SM at the same time and share the
-        // source-frame lines their gathers touch through L1
-        const int per_image = p.n_chunks * p.n_strips, per_pass = per_image * p.B;
-        const int slot = blockIdx.x % p.colocate, r = blockIdx.x / p.colocate;
-        pass_i = r % p.n_pass;
-        const int j = (r / p.n_pass) * p.colocate + slot;
-        if (j >= per_pass) return;
-        b = j / per_image;
-        bx = j - b * per_image;
-    }
-    const int chunk = bx / p.n_strips;
-    const int strip = bx - chunk * p.n_strips;
-    const int item = (pass_i * p.B + b) * (p.n_chunks * p.n_strips) + bx;
+    const int b = blockIdx.y, pass_i = blockIdx.z;
+    const int chunk = blockIdx.x / p.n_strips;
+    const int strip = blockIdx.x - chunk * p.n_strips;
+    const int item = (pass_i * p.B + b) * (p.n_chunks * p.n_strips) + blockIdx.x;
     const PassDev& ps = p.pass[pass_i];
 
     const int H = p.H, W = p.W, S = p.S;
