@@ -29,10 +29,13 @@ struct HeadParams {
 
 __device__ __forceinline__ float sigmoidf(float z) { return __fdiv_rn(1.0f, 1.0f + expf(-z)); }
 
-// grid = B * n_chunks * n_strips work items; G = blockDim.x / 32 warps per item, warp g convolves the channels
-// g, g + G, g + 2G, ... (the low-resolution heads have 64 / 128 channels over few pixels: without the split a
-// 24 x 80 map would occupy 72 warps of the whole GPU) and the partial pre-activations of a row meet in shared
-// memory, summed in warp order by warp 0.  Dynamic smem = C * 12 floats (weights) + G * 32 floats.
+// grid = B * ceil(h / kHeadFR) * n_strips work items of kHeadFR rows x 30 columns; G = blockDim.x / 32 warps per item, warp g
+// convolves the channels g, g + G, g + 2G, ... for the WHOLE item (the low-resolution heads have 64 / 128 channels over few
+// pixels: without the split a 24 x 80 map would occupy 72 warps of the whole GPU): the ten input rows of a channel are loaded
+// at once, the kHeadFR pre-activations stay in registers, and the warps meet in shared memory once, at the end (the first
+// version exchanged partial rows through shared memory with two block barriers per row and was slower than cuDNN on the
+// 24 x 80 head).  Dynamic smem = C * 12 floats (weights) + G * kHeadFR * 32 floats.
+constexpr int kHeadFR = 8;
 __global__ void __launch_bounds__(256)
 disp_head_fwd_kernel(const HeadParams p) {
     PML_DYN_SMEM(float, sw);
@@ -41,47 +44,58 @@ disp_head_fwd_kernel(const HeadParams p) {
     float* sred = sw + C * 12;
     for (int i = threadIdx.x; i < C * 9; i += blockDim.x) sw[(i / 9) * 12 + (i % 9)] = p.weight[i];
     __syncthreads();
+    const int n_rows = (h + kHeadFR - 1) / kHeadFR;
     int item = blockIdx.x;
     const int strip = item % p.n_strips; item /= p.n_strips;
-    const int chunk = item % p.n_chunks;
-    const int b = item / p.n_chunks;
+    const int chunk = item % n_rows;
+    const int b = item / n_rows;
     const int x0 = strip * kHeadTW, x1 = min(x0 + kHeadTW, w);
-    const int y0 = chunk * kHeadTH, y1 = min(y0 + kHeadTH, h);
+    const int y0 = chunk * kHeadFR;
     const int cx = x0 - 1 + lane;
     const int rx = reflect1(clampi(cx, -1, w), w);
     const bool owned = (cx >= x0) && (cx < x1);
-    const float bias = __ldg(p.bias);
     const float* xb = p.x + (size_t)b * C * plane + rx;
-    // a0 / a1 / a2: pre-activations of the windows centred on rows r-1, r, r+1 while row r streams through
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-#pragma unroll 1
-    for (int r = y0 - 1; r <= y1; ++r) {
-        const int ry = reflect1(clampi(r, -1, h), h);
-        const float* xr = xb + ry * w;
-#pragma unroll 4
-        for (int c = g; c < C; c += G) {
-            const float v = __ldg(xr + (size_t)c * plane);
-            const float l = __shfl_up_sync(0xffffffffu, v, 1), rr = __shfl_down_sync(0xffffffffu, v, 1);
-            const float4* wk = reinterpret_cast<const float4*>(sw + c * 12);
-            const float4 w0 = wk[0], w1 = wk[1], w2 = wk[2];   // W[0][0..2] W[1][0] | W[1][1..2] W[2][0..1] | W[2][2]
-            a2 = fmaf(w0.x, l, fmaf(w0.y, v, fmaf(w0.z, rr, a2)));   // row r is the top row of window r+1
-            a1 = fmaf(w0.w, l, fmaf(w1.x, v, fmaf(w1.y, rr, a1)));   // ... the middle row of window r
-            a0 = fmaf(w1.z, l, fmaf(w1.w, v, fmaf(w2.x, rr, a0)));   // ... the bottom row of window r-1
-        }
-        const int py = r - 1;
-        if (G > 1) {
-            sred[g * 32 + lane] = a0;
-            __syncthreads();
-            if (g == 0) {
-                float t = 0.f;
-                for (int k = 0; k < G; ++k) t += sred[k * 32 + lane];
-                if (owned && py >= y0 && py < y1) p.disp[(size_t)b * plane + py * w + cx] = sigmoidf(t + bias);
+    int ro[kHeadFR + 2];
+#pragma unroll
+    for (int j = 0; j < kHeadFR + 2; ++j) ro[j] = reflect1(clampi(y0 - 1 + j, -1, h), h) * w;
+    float a[kHeadFR];
+#pragma unroll
+    for (int i = 0; i < kHeadFR; ++i) a[i] = 0.f;
+#pragma unroll 2
+    for (int c = g; c < C; c += G) {
+        const float* xc = xb + (size_t)c * plane;
+        float v[kHeadFR + 2];
+#pragma unroll
+        for (int j = 0; j < kHeadFR + 2; ++j) v[j] = __ldg(xc + ro[j]);
+        const float4* wk = reinterpret_cast<const float4*>(sw + c * 12);
+        const float4 w0 = wk[0], w1 = wk[1], w2 = wk[2];   // W[0][0..2] W[1][0] | W[1][1..2] W[2][0..1] | W[2][2]
+        const float W[9] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x};
+#pragma unroll
+        for (int j = 0; j < kHeadFR + 2; ++j) {
+            const float l = __shfl_up_sync(0xffffffffu, v[j], 1), rr = __shfl_down_sync(0xffffffffu, v[j], 1);
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {      // input row j is tap row dy of output row j - dy
+                const int i = j - dy;
+                if (i >= 0 && i < kHeadFR) a[i] = fmaf(W[dy * 3], l, fmaf(W[dy * 3 + 1], v[j], fmaf(W[dy * 3 + 2], rr, a[i])));
             }
-            __syncthreads();
-        } else if (owned && py >= y0 && py < y1) {
-            p.disp[(size_t)b * plane + py * w + cx] = sigmoidf(a0 + bias);
         }
-        a0 = a1; a1 = a2; a2 = 0.f;
+    }
+    const float bias = __ldg(p.bias);
+    if (G > 1) {
+#pragma unroll
+        for (int i = 0; i < kHeadFR; ++i) sred[(g * kHeadFR + i) * 32 + lane] = a[i];
+        __syncthreads();
+        for (int t = threadIdx.x; t < kHeadFR * 32; t += blockDim.x) {      // (row i, lane): warps summed in warp order
+            const int i = t >> 5, ln = t & 31;
+            float s = 0.f;
+            for (int k = 0; k < G; ++k) s += sred[(k * kHeadFR + i) * 32 + ln];
+            const int ox = x0 - 1 + ln, oy = y0 + i;
+            if (ox >= x0 && ox < x1 && oy < h) p.disp[(size_t)b * plane + oy * w + ox] = sigmoidf(s + bias);
+        }
+    } else if (owned) {
+#pragma unroll
+        for (int i = 0; i < kHeadFR; ++i)
+            if (y0 + i < h) p.disp[(size_t)b * plane + (y0 + i) * w + cx] = sigmoidf(a[i] + bias);
     }
 }
 
