@@ -134,17 +134,27 @@ disp_head_bwd_kernel(const HeadParams p) {
 #pragma unroll
     for (int k = 0; k < 9; ++k) acc[k] = 0.f;
     float accb = 0.f;
+    // all rows of the item are requested before the first is consumed (the march used to wait for three loads per row)
+    float xs[kHeadTH + 2], gs[kHeadTH + 2];
+#pragma unroll
+    for (int j = 0; j < kHeadTH + 2; ++j) {
+        const int r = y0 - 1 + j;
+        xs[j] = 0.f; gs[j] = 0.f;
+        if (r <= y1) {
+            xs[j] = __ldg(xc + reflect1(clampi(r, -1, h), h) * w);
+            if (r >= 0 && r < h && in_img) {
+                const float d = __ldg(dd + r * w + cx);
+                gs[j] = __ldg(gd + r * w + cx) * d * (1.f - d);      // sigmoid backward
+            }
+        }
+    }
     // rolling rows r-2 (U), r-1 (M): folded gz neighbourhood (l', v, r') and x_pad neighbourhood (l, v, r)
     float gU[3] = {0.f, 0.f, 0.f}, gM[3] = {0.f, 0.f, 0.f}, xU[3] = {0.f, 0.f, 0.f}, xM[3] = {0.f, 0.f, 0.f};
-#pragma unroll 1
-    for (int r = y0 - 1; r <= y1; ++r) {
-        const int ry = reflect1(clampi(r, -1, h), h);
-        const float xv = __ldg(xc + ry * w);
-        float gz = 0.f;
-        if (r >= 0 && r < h && in_img) {
-            const float d = __ldg(dd + r * w + cx);
-            gz = __ldg(gd + r * w + cx) * d * (1.f - d);      // sigmoid backward
-        }
+#pragma unroll
+    for (int j = 0; j < kHeadTH + 2; ++j) {
+        const int r = y0 - 1 + j;
+        if (r > y1) break;
+        const float xv = xs[j], gz = gs[j];
         const float xl = __shfl_up_sync(0xffffffffu, xv, 1), xr = __shfl_down_sync(0xffffffffu, xv, 1);
         const float gl = __shfl_up_sync(0xffffffffu, gz, 1), gr = __shfl_down_sync(0xffffffffu, gz, 1);
         const float gD[3] = {gl + f2 * gr, gz, gr + f1 * gl};
